@@ -1,0 +1,147 @@
+"""CPU tests: the oracle restatement (oracle/cvt_oracle.c) against the committed golden vectors,
+which were produced by the UNMODIFIED reference compiled in place (oracle/gen_golden.py), and --
+when this container still has /root/reference and oracle/_ref -- against the reference itself."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from cvt_b200 import synth
+from oracle import oracle as orc
+
+G = cases.GOLDEN
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _check_opq(gold, prefix, coarse, cb, reorder, db_rows, q_rows, nk):
+    g = lambda k: gold[prefix + k]
+    x = orc.opq_reorder(db_rows, reorder)
+    lists = orc.opq_coarse_assign(x, coarse)
+    assert np.array_equal(lists, g("row_list"))
+    codes = orc.opq_pq_encode(x, coarse, lists, cb)
+    assert np.array_equal(codes, g("codes"))
+    qr = orc.opq_reorder(q_rows, reorder)
+    n_groups = int(gold[prefix + "n_groups"])
+    match = orc.opq_query_scores(qr, coarse, cb, nk, lists, g("row_group"), codes, n_groups, 1.0)
+    assert np.array_equal(_bits(match), _bits(g("match")))
+    k = int(gold[prefix + "topk"])
+    for f in range(match.shape[0]):
+        s, i = orc.topk_pairs(match[f], k)
+        assert np.array_equal(i, g("topk_id")[f])
+        assert np.array_equal(_bits(s), _bits(g("topk_score")[f]))
+
+
+def _fixture_rows():
+    db = np.concatenate([np.fromfile(os.path.join(G, "opq_fixture", "db", f), dtype="<f4").reshape(-1, 128)
+                         for f in cases.FIXTURE_DB])
+    q = np.concatenate([np.fromfile(os.path.join(G, "opq_fixture", "query", f), dtype="<f4").reshape(-1, 128)
+                        for f in cases.FIXTURE_QUERY])
+    return db, q
+
+
+def test_shipped_fixture_reduced_model():
+    gold = np.load(os.path.join(G, "opq_shipped_k256.npz"))
+    coarse, cb, reorder = synth.read_opq_model(os.path.join(G, "opq_shipped_k256.model"))
+    db, q = _fixture_rows()
+    assert db.shape == (53, 128) and q.shape == (10, 128)
+    _check_opq(gold, "", coarse, cb, reorder, db, q, 3)
+    _check_opq(gold, "pr_", coarse, cb, reorder, db, q, 3)
+    # SURVEY.md App. C known answers (produced by the reference on the FULL shipped model; the
+    # reduced model reproduces them because it keeps every centroid that can win)
+    assert hashlib.sha256(gold["codes"].tobytes()).hexdigest() == \
+        "9896a9b07826dadf9ae06a9159a2d37e2a1712bfc1d5456163de41e37338c3c7"
+    assert gold["codes"][0].tolist() == [232, 88, 97, 41, 245, 248, 61, 222, 180, 193, 190, 48, 7, 128, 24, 86]
+    np.testing.assert_allclose(gold["match"][2], [0.13036789, 0.766138613, 0.670435786, 0.666301548, 0.827702045],
+                               rtol=1e-7)
+    assert gold["file_topk_id"][0].tolist() == [0, 2, 3, 1, 4]
+    np.testing.assert_allclose(gold["file_topk_score"][0], [1.25004315, 7.37535906, 7.3803978, 7.61460876, 7.98865891],
+                               rtol=1e-7)
+    assert gold["file_topk_id"][1].tolist() == [0, 1, 2, 3, 4]  # clamp ties at 1.0 broken by id
+
+
+@pytest.mark.skipif(not os.path.isdir(orc.REFERENCE_ROOT), reason="full shipped model only in the build container")
+def test_shipped_fixture_full_model():
+    gold = np.load(os.path.join(G, "opq_shipped_full.npz"))
+    model = os.path.join(orc.REFERENCE_ROOT, "opq/model/OPQ_db_5950000_dim_128_k_8192_PQ_m16_k256_reorder.model")
+    assert hashlib.sha256(open(model, "rb").read()).hexdigest() == str(gold["model_sha256"])
+    coarse, cb, reorder = synth.read_opq_model(model)
+    db, q = _fixture_rows()
+    _check_opq(gold, "", coarse, cb, reorder, db, q, 3)
+    assert gold["row_list"][:9].tolist() == [1955, 1955, 1870, 1870, 1870, 5812, 5812, 71, 6987]
+
+
+@pytest.mark.parametrize("name", list(cases.OPQ_CASES))
+def test_opq_synthetic(name):
+    c = cases.opq_case(name)
+    gold = np.load(os.path.join(G, f"opq_{name}.npz"))
+    assert str(gold["input_sha"]) == c["input_sha"], "input generator drifted; regenerate goldens"
+    _check_opq(gold, "", c["coarse"], c["cb"], c["reorder"], c["db"], c["q"], c["nk"])
+
+
+@pytest.mark.parametrize("name", list(cases.FLAT_CASES))
+def test_flat(name):
+    c = cases.flat_case(name)
+    gold = np.load(os.path.join(G, f"flat_{name}.npz"))
+    assert str(gold["input_sha"]) == c["input_sha"]
+    runs = {"ip_sse": (0, 4), "ip_hnsw": (0, 4), "ip_avx": (0, 8), "l2_avx": (1, 8), "l2_sse": (1, 4), "l2i": (2, 0)}
+    seen = 0
+    for tag, (metric, lanes) in runs.items():
+        if tag + "_dist" not in gold:
+            continue
+        seen += 1
+        data, q = (c["xu"], c["qu"]) if metric == 2 else (c["x"], c["q"])
+        d, l = orc.flat_search(metric, lanes, data, c["labels"], q, c["k"])
+        assert np.array_equal(l, gold[tag + "_label"]), tag
+        assert np.array_equal(_bits(d), _bits(gold[tag + "_dist"])), tag
+    assert seen >= 4
+
+
+def test_flat_tie_rule_is_lexicographic():
+    # brutoforce.hpp:81-91 keeps the k smallest under (dist, label)
+    c = cases.flat_case("ties_d16")
+    d, l = orc.flat_search(0, 4, c["x"], c["labels"], c["q"], c["k"])
+    for i in range(c["nq"]):
+        alld = np.array([orc.lib().orc_flat_ip(orc._p(c["q"][i]), orc._p(c["x"][j]), 16, 4) for j in range(c["n"])],
+                        dtype=np.float32)
+        order = np.lexsort((c["labels"], alld))[:c["k"]]
+        assert np.array_equal(c["labels"][order], l[i])
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_sq_restatement_self_consistency(d):
+    # parity UNPINNED at the faiss boundary (no model shipped, faiss un-vendored): the golden is the
+    # restatement's own output; this guards against drift and checks the documented properties.
+    c = cases.sq_case(d)
+    gold = np.load(os.path.join(G, f"sq_d{d}.npz"))
+    assert str(gold["input_sha"]) == c["input_sha"]
+    codes, xn = orc.sq_encode(c["x"], c["vmin"], c["vdiff"], True)
+    assert np.array_equal(codes, gold["codes"])
+    assert np.array_equal(_bits(xn), _bits(gold["x_normed"]))
+    dec = orc.sq_decode(codes, c["vmin"], c["vdiff"])
+    assert np.array_equal(_bits(dec), _bits(gold["decode"]))
+    decf = orc.sq_decode(codes, c["vmin"], c["vdiff"], faiss_float=True)
+    assert np.array_equal(_bits(decf), _bits(gold["decode_faiss"]))
+    # properties: all-zero row stays zero; constant dim (vdiff==0) encodes 0; decode error <= half a bucket
+    assert np.all(xn[1] == 0) and np.all(codes[:, 3] == 0)
+    inside = (xn >= c["vmin"]) & (xn <= c["vmin"] + c["vdiff"])
+    err = np.abs(dec - xn)[inside]
+    bucket = np.broadcast_to(c["vdiff"] / 255.0, xn.shape)[inside]
+    assert np.all(err <= bucket * 1.0 + 1e-6)
+    vmin, vdiff = orc.sq_train_minmax(xn)
+    assert np.array_equal(vmin, xn.min(0)) and np.array_equal(vdiff, xn.max(0) - xn.min(0))
+
+
+@pytest.mark.skipif(not orc.have_ref("ref_opq"), reason="oracle/_ref not built")
+def test_reference_binary_agrees_with_golden(tmp_path):
+    # the compiled reference travels to the GPU box; make sure it still reproduces the goldens there
+    gold = np.load(os.path.join(G, "opq_shipped_k256.npz"))
+    gdb = [os.path.join(G, "opq_fixture", "db", f) for f in cases.FIXTURE_DB]
+    gq = [os.path.join(G, "opq_fixture", "query", f) for f in cases.FIXTURE_QUERY]
+    r = orc.run_ref_opq(os.path.join(G, "opq_shipped_k256.model"), gdb, gq, nk=3, topk=5, per_row=False)
+    assert np.array_equal(r["codes"], gold["codes"])
+    assert np.array_equal(_bits(r["match"]), _bits(gold["match"]))
