@@ -1,0 +1,96 @@
+"""In-tree build of the CUDA library and the C++ tools: plain nvcc for sm_100a, no JIT cache.
+
+    python -m cvt_b200.build            # incremental
+    python -m cvt_b200.build --force
+
+Outputs (git-ignored, but they travel with the gpurun snapshot):
+    cvt_b200/lib/libb200nn.so      -- the C-ABI shared library declared in include/b200nn.h
+    tools/bin/*                    -- C++ programs written against the drop-in headers
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIBDIR = os.path.join(PKG, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIB = os.path.join(LIBDIR, "libb200nn.so")
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+              "--expt-relaxed-constexpr"]
+
+
+def _newer(src_paths, out) -> bool:
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in src_paths)
+
+
+def _run(cmd, log):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    jobs = []
+    objs = []
+    for s in srcs:
+        o = os.path.join(OBJDIR, os.path.basename(s)[:-3] + ".o")
+        objs.append(o)
+        if force or _newer([s] + headers, o):
+            jobs.append(([NVCC] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", s, "-o", o], o + ".log"))
+    if jobs:
+        if verbose:
+            print(f"[build] compiling {len(jobs)} CUDA translation unit(s) for sm_100a")
+        with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(lambda j: _run(*j), jobs))
+    if force or jobs or not os.path.exists(LIB):
+        _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs, os.path.join(OBJDIR, "link.log"))
+    return LIB
+
+
+def build_tools(force: bool = False, verbose: bool = False):
+    """C++ programs written against include/b200nn/*.hpp (the reference-facing classes)."""
+    tdir = os.path.join(ROOT, "tools")
+    bdir = os.path.join(tdir, "bin")
+    os.makedirs(bdir, exist_ok=True)
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    outs = []
+    hdrs = glob.glob(os.path.join(ROOT, "include", "**", "*"), recursive=True)
+    hdrs = [h for h in hdrs if os.path.isfile(h)]
+    for s in sorted(glob.glob(os.path.join(tdir, "*.cpp"))):
+        o = os.path.join(bdir, os.path.basename(s)[:-4])
+        outs.append(o)
+        if force or _newer([s, LIB] + hdrs, o):
+            _run([gxx, "-O2", "-std=c++14", "-I", os.path.join(ROOT, "include"), s, "-o", o, "-L", LIBDIR, "-lb200nn",
+                  "-Wl,-rpath," + LIBDIR], o + ".log")
+    return outs
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    lib = build_lib(force, verbose)
+    tools = build_tools(force, verbose)
+    return lib, tools
+
+
+if __name__ == "__main__":
+    lib, tools = build_all(force="--force" in sys.argv, verbose=True)
+    print(lib)
+    for t in tools:
+        print(t)

@@ -1,0 +1,253 @@
+"""ctypes binding of the C ABI (include/b200nn.h) -- the same entry points a cgo/JNI/C++ caller
+binds.  Used by the tests and bench.py; numpy arrays are HOST buffers, `*_dev` methods take raw
+device pointers (e.g. torch tensors' data_ptr()).
+
+There is no fallback: if the CUDA library has not been built, or no B200 is present, loading /
+context creation raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libb200nn.so")
+
+# every symbol include/b200nn.h declares (tests check that the built library exports them all)
+SYMBOLS = [
+    "b200nn_last_error", "b200nn_version", "b200nn_ctx_create", "b200nn_ctx_destroy", "b200nn_ctx_set_stream",
+    "b200nn_ctx_synchronize", "b200nn_ctx_launch_count", "b200nn_ctx_event_record", "b200nn_ctx_event_elapsed_ms",
+    "b200nn_flat_create", "b200nn_flat_destroy", "b200nn_flat_add", "b200nn_flat_remove", "b200nn_flat_size",
+    "b200nn_flat_search", "b200nn_flat_search_dev", "b200nn_flat_save", "b200nn_flat_load",
+    "b200nn_pq_create", "b200nn_pq_load_model", "b200nn_pq_destroy", "b200nn_pq_set_clamp", "b200nn_pq_info",
+    "b200nn_pq_rotate", "b200nn_pq_encode", "b200nn_pq_add", "b200nn_pq_add_dev", "b200nn_pq_get_rows",
+    "b200nn_pq_build_lut", "b200nn_pq_scores", "b200nn_pq_search", "b200nn_pq_search_dev", "b200nn_topk_merge_dev",
+    "b200nn_pq_save_index", "b200nn_pq_load_index", "b200nn_pq_last_timing", "b200nn_pq_scan_bytes",
+    "b200nn_sq_create", "b200nn_sq_destroy", "b200nn_sq_train_minmax", "b200nn_sq_encode", "b200nn_sq_decode",
+    "b200nn_sq_encode_dev",
+]
+
+_lib = None
+
+
+class B200nnError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the in-tree library; raises if it was not built (python -m cvt_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200nnError(f"{LIB_PATH} is missing: build it with `python -m cvt_b200.build` (no CPU fallback exists)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.b200nn_last_error.restype = C.c_char_p
+        _lib.b200nn_version.restype = C.c_char_p
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise B200nnError(f"{what} failed ({rc}): {load().b200nn_last_error().decode(errors='replace')}")
+
+
+def _vp(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.h = C.c_void_p()
+        _check(load().b200nn_ctx_create(C.c_int(device), C.byref(self.h)), "ctx_create")
+        self.device = device
+        self._children = []  # weakrefs: indexes must be destroyed before their context
+
+    def _adopt(self, child):
+        self._children.append(weakref.ref(child))
+
+    def close(self):
+        if self.h:
+            for r in self._children:
+                ch = r()
+                if ch is not None:
+                    ch.close()
+            self._children = []
+            load().b200nn_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        _check(load().b200nn_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)), "ctx_set_stream")
+
+    def synchronize(self):
+        _check(load().b200nn_ctx_synchronize(self.h), "ctx_synchronize")
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        _check(load().b200nn_ctx_launch_count(self.h, C.byref(v)), "ctx_launch_count")
+        return int(v.value)
+
+    def event_record(self, slot: int):
+        _check(load().b200nn_ctx_event_record(self.h, C.c_int(slot)), "ctx_event_record")
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        _check(load().b200nn_ctx_event_elapsed_ms(self.h, C.c_int(a), C.c_int(b), C.byref(ms)), "ctx_event_elapsed_ms")
+        return float(ms.value)
+
+    def topk_merge_dev(self, keys_dev: int, L: int, nq: int, k: int, out_dist_dev: int, out_id_dev: int):
+        _check(load().b200nn_topk_merge_dev(self.h, C.c_void_p(keys_dev), C.c_int(L), C.c_size_t(nq), C.c_size_t(k),
+                                            C.c_void_p(out_dist_dev), C.c_void_p(out_id_dev)), "topk_merge_dev")
+
+
+class PQIndex:
+    """IVFOPQ drop-in surface (opq/src/IVFOPQ.h:31-47) over the C ABI."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+        ctx._adopt(self)
+        D, K, M, ks = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(load().b200nn_pq_info(self.h, C.byref(D), C.byref(K), C.byref(M), C.byref(ks), None, None), "pq_info")
+        self.D, self.K, self.M, self.ksub = D.value, K.value, M.value, ks.value
+
+    @classmethod
+    def create(cls, ctx, coarse, codebooks, perm=None, R=None, clamp=1.0):
+        coarse, codebooks = _f32(coarse), _f32(codebooks)
+        K, D = coarse.shape
+        M, ksub, ds = codebooks.shape
+        assert M * ds == D
+        perm_a = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        R_a = None if R is None else _f32(R)
+        h = C.c_void_p()
+        _check(load().b200nn_pq_create(ctx.h, C.c_int(D), C.c_int(K), C.c_int(M), C.c_int(ksub), _vp(coarse), _vp(codebooks),
+                                       _vp(perm_a), _vp(R_a), C.c_float(clamp), C.byref(h)), "pq_create")
+        return cls(ctx, h)
+
+    @classmethod
+    def load_model(cls, ctx, path: str):
+        h = C.c_void_p()
+        _check(load().b200nn_pq_load_model(ctx.h, path.encode(), C.byref(h)), "pq_load_model")
+        return cls(ctx, h)
+
+    @classmethod
+    def load_index(cls, ctx, path: str, perm=None, clamp=1.0):
+        perm_a = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        h = C.c_void_p()
+        _check(load().b200nn_pq_load_index(ctx.h, path.encode(), _vp(perm_a), C.c_float(clamp), C.byref(h)), "pq_load_index")
+        return cls(ctx, h)
+
+    def close(self):
+        if self.h:
+            load().b200nn_pq_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_clamp(self, clamp: float):
+        _check(load().b200nn_pq_set_clamp(self.h, C.c_float(clamp)), "pq_set_clamp")
+
+    @property
+    def n_rows(self) -> int:
+        v = C.c_uint64()
+        _check(load().b200nn_pq_info(self.h, None, None, None, None, C.byref(v), None), "pq_info")
+        return int(v.value)
+
+    @property
+    def n_groups(self) -> int:
+        v = C.c_uint64()
+        _check(load().b200nn_pq_info(self.h, None, None, None, None, None, C.byref(v)), "pq_info")
+        return int(v.value)
+
+    def rotate(self, x):
+        x = _f32(x)
+        y = np.empty_like(x)
+        _check(load().b200nn_pq_rotate(self.h, _vp(x), C.c_size_t(x.shape[0]), _vp(y)), "pq_rotate")
+        return y
+
+    def encode(self, x_rot):
+        x_rot = _f32(x_rot)
+        n = x_rot.shape[0]
+        lists = np.empty(n, dtype=np.int32)
+        codes = np.empty((n, self.M), dtype=np.uint8)
+        _check(load().b200nn_pq_encode(self.h, _vp(x_rot), C.c_size_t(n), _vp(lists), _vp(codes)), "pq_encode")
+        return lists, codes
+
+    def add(self, x_raw, group_ids=None):
+        x_raw = _f32(x_raw)
+        g = None if group_ids is None else np.ascontiguousarray(group_ids, dtype=np.int32)
+        _check(load().b200nn_pq_add(self.h, _vp(x_raw), C.c_size_t(x_raw.shape[0]), _vp(g)), "pq_add")
+
+    def add_dev(self, x_dev_ptr: int, n: int, group_dev_ptr: int | None = None):
+        _check(load().b200nn_pq_add_dev(self.h, C.c_void_p(x_dev_ptr), C.c_size_t(n), C.c_void_p(group_dev_ptr or 0)), "pq_add_dev")
+
+    def get_rows(self, start=0, n=None):
+        n = self.n_rows - start if n is None else n
+        lists = np.empty(n, dtype=np.int32)
+        groups = np.empty(n, dtype=np.int32)
+        codes = np.empty((n, self.M), dtype=np.uint8)
+        _check(load().b200nn_pq_get_rows(self.h, C.c_uint64(start), C.c_size_t(n), _vp(lists), _vp(groups), _vp(codes)), "pq_get_rows")
+        return lists, groups, codes
+
+    def build_lut(self, q_rot, nprobe=1):
+        q_rot = _f32(q_rot)
+        nq = q_rot.shape[0]
+        lists = np.empty((nq, nprobe), dtype=np.int32)
+        lut = np.empty((nq, nprobe, self.M, self.ksub), dtype=np.float32)
+        _check(load().b200nn_pq_build_lut(self.h, _vp(q_rot), C.c_size_t(nq), C.c_int(nprobe), _vp(lists), _vp(lut)), "pq_build_lut")
+        return lists, lut
+
+    def scores(self, q_raw, nprobe=3):
+        q_raw = _f32(q_raw)
+        out = np.empty((q_raw.shape[0], self.n_groups), dtype=np.float32)
+        _check(load().b200nn_pq_scores(self.h, _vp(q_raw), C.c_size_t(q_raw.shape[0]), C.c_int(nprobe), _vp(out)), "pq_scores")
+        return out
+
+    def search(self, q_raw, k, nprobe=1):
+        q_raw = _f32(q_raw)
+        nq = q_raw.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.uint64)
+        _check(load().b200nn_pq_search(self.h, _vp(q_raw), C.c_size_t(nq), C.c_int(nprobe), C.c_size_t(k), _vp(D), _vp(I)), "pq_search")
+        return D, I
+
+    def search_host_ptr(self, q_ptr: int, nq: int, k: int, nprobe: int, out_dist_ptr: int, out_id_ptr: int):
+        """Same call as search() with caller-owned (e.g. pinned) HOST buffers."""
+        _check(load().b200nn_pq_search(self.h, C.c_void_p(q_ptr), C.c_size_t(nq), C.c_int(nprobe), C.c_size_t(k),
+                                       C.c_void_p(out_dist_ptr), C.c_void_p(out_id_ptr)), "pq_search")
+
+    def search_dev(self, q_dev_ptr: int, nq: int, k: int, nprobe: int, out_dist_ptr: int, out_id_ptr: int, out_key_ptr: int = 0,
+                   id_base: int = 0):
+        _check(load().b200nn_pq_search_dev(self.h, C.c_void_p(q_dev_ptr), C.c_size_t(nq), C.c_int(nprobe), C.c_size_t(k),
+                                           C.c_void_p(out_dist_ptr), C.c_void_p(out_id_ptr), C.c_void_p(out_key_ptr),
+                                           C.c_uint64(id_base)), "pq_search_dev")
+
+    def last_timing(self):
+        ms = (C.c_float * 4)()
+        _check(load().b200nn_pq_last_timing(self.h, ms), "pq_last_timing")
+        return dict(rotate_ms=ms[0], lut_ms=ms[1], scan_ms=ms[2], merge_ms=ms[3])
+
+    def save_index(self, dir_or_path: str, group_paths=None):
+        arr = None
+        if group_paths is not None:
+            arr = (C.c_char_p * len(group_paths))(*[p.encode() for p in group_paths])
+        _check(load().b200nn_pq_save_index(self.h, dir_or_path.encode(), arr), "pq_save_index")

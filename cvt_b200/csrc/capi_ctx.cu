@@ -1,0 +1,96 @@
+// capi_ctx.cu -- context, error reporting, stream/event plumbing of the C ABI.
+#include "capi_common.cuh"
+#include "topk.cuh"
+
+namespace b200nn {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace b200nn
+
+using namespace b200nn;
+
+extern "C" {
+
+const char* b200nn_last_error(void) { return g_last_error.c_str(); }
+const char* b200nn_version(void) { return "b200nn 0.1 (sm_100a)"; }
+
+int b200nn_ctx_create(int device, b200nn_ctx_t* out) {
+    if (!out) B2_FAIL(B200NN_ERR_INVALID, "ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        B2_FAIL(B200NN_ERR_CUDA, std::string("ctx_create: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) B2_FAIL(B200NN_ERR_INVALID, "ctx_create: bad device ordinal");
+    B2_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        B2_FAIL(B200NN_ERR_UNSUPPORTED, std::string("ctx_create: this library is built for sm_100a only; device is sm_") +
+                                            std::to_string(prop.major) + std::to_string(prop.minor));
+    b200nn_ctx* c = new b200nn_ctx();
+    c->c.device = device;
+    c->c.sm_count = prop.multiProcessorCount;
+    c->c.smem_optin = prop.sharedMemPerBlockOptin;
+    B2_CUDA(cudaStreamCreateWithFlags(&c->c.own_stream, cudaStreamNonBlocking));
+    c->c.stream = c->c.own_stream;
+    for (int i = 0; i < 16; i++) B2_CUDA(cudaEventCreate(&c->c.events[i]));
+    B2_CUDA(cudaMalloc(&c->c.d_err, sizeof(int)));
+    B2_CUDA(cudaMemset(c->c.d_err, 0, sizeof(int)));
+    *out = c;
+    return 0;
+}
+
+void b200nn_ctx_destroy(b200nn_ctx_t ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    for (int i = 0; i < 16; i++)
+        if (ctx->c.events[i]) cudaEventDestroy(ctx->c.events[i]);
+    if (ctx->c.d_err) cudaFree(ctx->c.d_err);
+    if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.own_stream);
+    delete ctx;
+}
+
+int b200nn_ctx_set_stream(b200nn_ctx_t ctx, void* cuda_stream) {
+    if (!ctx) B2_FAIL(B200NN_ERR_INVALID, "ctx is NULL");
+    B2_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    ctx->c.stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->c.own_stream;
+    return 0;
+}
+
+int b200nn_ctx_synchronize(b200nn_ctx_t ctx) {
+    if (!ctx) B2_FAIL(B200NN_ERR_INVALID, "ctx is NULL");
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    B2_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return 0;
+}
+
+int b200nn_ctx_launch_count(b200nn_ctx_t ctx, uint64_t* out) {
+    if (!ctx || !out) B2_FAIL(B200NN_ERR_INVALID, "ctx/out is NULL");
+    *out = ctx->c.launches;
+    return 0;
+}
+
+int b200nn_ctx_event_record(b200nn_ctx_t ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 8) B2_FAIL(B200NN_ERR_INVALID, "event slot must be in [0,8)");
+    B2_CUDA(cudaEventRecord(ctx->c.events[8 + slot], ctx->c.stream));
+    return 0;
+}
+
+int b200nn_ctx_event_elapsed_ms(b200nn_ctx_t ctx, int a, int b, float* ms) {
+    if (!ctx || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) B2_FAIL(B200NN_ERR_INVALID, "bad event slot");
+    B2_CUDA(cudaEventSynchronize(ctx->c.events[8 + b]));
+    B2_CUDA(cudaEventElapsedTime(ms, ctx->c.events[8 + a], ctx->c.events[8 + b]));
+    return 0;
+}
+
+int b200nn_topk_merge_dev(b200nn_ctx_t ctx, const uint64_t* keys_dev, int L, size_t nq, size_t k, float* out_dist_dev,
+                          uint64_t* out_id_dev) {
+    if (!ctx || !keys_dev || L < 1 || k < 1) B2_FAIL(B200NN_ERR_INVALID, "topk_merge: bad arguments");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    return launch_topk_merge(&ctx->c, (const unsigned long long*)keys_dev, L, (long long)nq, (int)k, (long long)(nq * k),
+                             out_dist_dev, nullptr, (unsigned long long*)out_id_dev, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,778 @@
+// pq_kernels.cu -- (O)PQ / IVFOPQ hot path on sm_100a:
+//   rotate (permutation gather), coarse assign, PQ argmin encode, LUT build, the TMA-staged
+//   conflict-free ADC scan with fused exact top-k, and the generic IVF (list-probing) scan.
+//
+// Arithmetic contract: every squared distance is the reference's sequential
+// fp32 loop `tmp = a-b; acc += tmp*tmp` (IVFOPQ.cpp:117-122,147-154,283-288) written with
+// __fsub_rn/__fmul_rn/__fadd_rn so nothing is contracted into FMAs; every ADC score is the
+// sequential fp32 sum over m = 0..M-1 starting from 0.0f (IVFOPQ.cpp:302-306).  Codes, LUTs and
+// scores are therefore bit-identical to the reference's.
+#include "pq_kernels.cuh"
+#include "topk.cuh"
+
+namespace b200nn {
+
+// =============================================================================================
+// a1. rotation as a permutation: y[r][i] = x[r][perm[i]]   (IVFOPQ::reorder, IVFOPQ.cpp:424-439)
+// =============================================================================================
+__global__ void rotate_perm_kernel(const float* __restrict__ x, long long n, int D, const int* __restrict__ perm,
+                                   float* __restrict__ y) {
+    const long long total = n * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / D;
+        const int c = (int)(i - r * D);
+        y[i] = __ldg(x + r * D + perm[c]);
+    }
+}
+
+// =============================================================================================
+// a2. coarse assignment: argmin_i sum_j (x_j - C[i][j])^2, first minimum wins
+//     (IVFOPQ::Add, IVFOPQ.cpp:107-129).  One warp per row; lane l evaluates centroids
+//     l, l+32, ... (each a sequential fp32 sum), then a warp-shuffle argmin on (dist, index).
+//     coarseT is the centroid table transposed to [D][K] so that lanes read consecutive addresses.
+// =============================================================================================
+__device__ __forceinline__ void warp_argmin(float& best, int& idx) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, s);
+        // lexicographic (dist, index): identical to the sequential strict-'<' first-min rule.
+        // idx == -1 marks "nothing beat UINT_MAX yet" and never wins against a real index.
+        const bool take = (oi >= 0) && (idx < 0 || ob < best || (ob == best && oi < idx));
+        if (take) { best = ob; idx = oi; }
+    }
+}
+
+__global__ void coarse_assign_kernel(const float* __restrict__ x, long long n, int D, const float* __restrict__ coarseT,
+                                     int K, int* __restrict__ out_list) {
+    extern __shared__ float s_x[];  // [warps][D]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* xr = s_x + w * D;
+    for (long long row = (long long)blockIdx.x * nw + w; row < n; row += (long long)gridDim.x * nw) {
+        for (int j = lane; j < D; j += 32) xr[j] = x[row * D + j];
+        __syncwarp();
+        float best = 4294967296.0f;  // (float)UINT_MAX, IVFOPQ.cpp:111
+        int idx = -1;
+        for (int c = lane; c < K; c += 32) {
+            float acc = 0.0f;
+            for (int j = 0; j < D; j++) {
+                const float t = __fsub_rn(xr[j], __ldg(coarseT + (long long)j * K + c));
+                acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
+            if (acc < best) { best = acc; idx = c; }
+        }
+        warp_argmin(best, idx);
+        if (lane == 0) out_list[row] = idx;
+        __syncwarp();
+    }
+}
+
+// =============================================================================================
+// a3. residual + PQ argmin encode (IVFOPQ::Add, IVFOPQ.cpp:135-163).  One warp per (row, m):
+//     lane l evaluates codewords l, l+32, ... sequentially over d_sub, then shuffle argmin.
+//     cbT = codebooks transposed to [M][d_sub][ksub] (lanes read consecutive codewords).
+// =============================================================================================
+template <int DS>
+__global__ void pq_encode_kernel(const float* __restrict__ x, long long n, int D, const float* __restrict__ coarse,
+                                 const int* __restrict__ list, const float* __restrict__ cbT, int M, int ksub,
+                                 unsigned char* __restrict__ codes) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = n * M;
+    for (long long p = warp; p < total; p += nwarps) {
+        const long long row = p / M;
+        const int m = (int)(p - row * M);
+        const int vw = list[row];
+        float res[DS];
+#pragma unroll
+        for (int k = 0; k < DS; k++)  // feat_residual = x - centroid, IVFOPQ.cpp:136-139
+            res[k] = __fsub_rn(__ldg(x + row * D + m * DS + k), __ldg(coarse + (long long)(vw < 0 ? 0 : vw) * D + m * DS + k));
+        float best = 4294967296.0f;  // (float)UINT_MAX, IVFOPQ.cpp:143
+        int idx = -1;
+        const float* cb = cbT + (long long)m * DS * ksub;
+        for (int j = lane; j < ksub; j += 32) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < DS; k++) {
+                const float t = __fsub_rn(res[k], __ldg(cb + k * ksub + j));
+                acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
+            if (acc < best) { best = acc; idx = j; }
+        }
+        warp_argmin(best, idx);
+        if (lane == 0) codes[p] = (unsigned char)idx;  // elem.PQindex[i] = vw1, IVFOPQ.cpp:161
+    }
+}
+
+// =============================================================================================
+// Scan layout of the coded database in HBM.  Rows are grouped in granules of 64; inside a
+// granule the M = 4G code bytes of a row are split into G little-endian 32-bit words (word h =
+// bytes of sub-quantizers 4h..4h+3) and stored plane-major:
+//     codesT[granule][h][row_in_granule]   (uint32)
+// so that the scan can move one plane of a stage with a single 1-D TMA copy and a lane group can
+// fetch the words of 4 consecutive rows with one 16-byte shared-memory load.  Rows beyond n are
+// zero bytes.
+// =============================================================================================
+__global__ void codes_to_scan_layout_kernel(const unsigned char* __restrict__ codes, long long n, int M,
+                                            uint32_t* __restrict__ codesT, long long n_pad) {
+    const int G = M / 4;
+    const long long total = n_pad * G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long gran = i / (64 * G);
+        const int rem = (int)(i - gran * 64 * G);
+        const int h = rem / 64, r = rem - h * 64;
+        const long long row = gran * 64 + r;
+        uint32_t w = 0;
+        if (row < n) {
+            const unsigned char* c = codes + row * M + 4 * h;
+            w = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
+        }
+        codesT[i] = w;
+    }
+}
+
+// =============================================================================================
+// a4. coarse probe selection (IVFOPQ::Query, IVFOPQ.cpp:238-260): the nk smallest centroids under
+//     (dist, index), emitted in the reference's pop order (largest first).  One warp per query.
+// =============================================================================================
+__global__ void coarse_probe_kernel(const float* __restrict__ q, long long nq, int D, const float* __restrict__ coarseT,
+                                    int K, int nk, int* __restrict__ out_lists) {
+    extern __shared__ float s_q[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* xr = s_q + w * D;
+    constexpr int MAXNK = 8;
+    for (long long row = (long long)blockIdx.x * nw + w; row < nq; row += (long long)gridDim.x * nw) {
+        for (int j = lane; j < D; j += 32) xr[j] = q[row * D + j];
+        __syncwarp();
+        float bd[MAXNK];
+        int bi[MAXNK];
+#pragma unroll
+        for (int t = 0; t < MAXNK; t++) { bd[t] = __int_as_float(0x7f800000); bi[t] = 0x7fffffff; }
+        for (int c = lane; c < K; c += 32) {
+            float acc = 0.0f;
+            for (int j = 0; j < D; j++) {
+                const float t = __fsub_rn(xr[j], __ldg(coarseT + (long long)j * K + c));
+                acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
+            // insert into the lane-local ascending list (indices ascend, so ties keep order)
+            float d = acc; int id = c;
+#pragma unroll
+            for (int t = 0; t < MAXNK; t++) {
+                if (t < nk && (d < bd[t] || (d == bd[t] && id < bi[t]))) {
+                    const float td = bd[t]; const int ti = bi[t];
+                    bd[t] = d; bi[t] = id; d = td; id = ti;
+                }
+            }
+        }
+        // pop the global minimum nk times
+        for (int r = 0; r < nk; r++) {
+            float d = bd[0]; int id = bi[0];
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, d, s);
+                const int oi = __shfl_xor_sync(0xffffffffu, id, s);
+                if (od < d || (od == d && oi < id)) { d = od; id = oi; }
+            }
+            if (bi[0] == id && bd[0] == d) {  // the owning lane advances its list
+#pragma unroll
+                for (int t = 0; t + 1 < MAXNK; t++) { bd[t] = bd[t + 1]; bi[t] = bi[t + 1]; }
+                bd[MAXNK - 1] = __int_as_float(0x7f800000); bi[MAXNK - 1] = 0x7fffffff;
+            }
+            if (lane == 0) out_lists[row * nk + (nk - 1 - r)] = id;  // reference pops largest first
+        }
+        __syncwarp();
+    }
+}
+
+// =============================================================================================
+// a5. residual + LUT build (IVFOPQ::Query, IVFOPQ.cpp:269-291).  One thread per (m, j) entry,
+//     sequential over d_sub.  Two output layouts:
+//       standard  lut[q][probe][m][j]
+//       scan      lut_scan[qgroup][pair][j][msel][lane]  (see adc_scan_topk_kernel)
+// =============================================================================================
+template <int DS>
+__global__ void lut_build_std_kernel(const float* __restrict__ q, long long nq, int D, const int* __restrict__ probes,
+                                     int nprobe, const float* __restrict__ coarse, const float* __restrict__ cb, int M,
+                                     int ksub, float* __restrict__ lut) {
+    extern __shared__ float s_res[];  // [D]
+    const long long qp = blockIdx.x;  // query * nprobe + probe
+    const long long qi = qp / nprobe;
+    const int vw = probes ? probes[qp] : 0;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) s_res[j] = __fsub_rn(q[qi * D + j], coarse[(long long)vw * D + j]);
+    __syncthreads();
+    for (int e = threadIdx.x; e < M * ksub; e += blockDim.x) {
+        const int m = e / ksub, j = e - m * ksub;
+        const float* c = cb + ((long long)m * ksub + j) * DS;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DS; k++) {
+            const float t = __fsub_rn(s_res[m * DS + k], __ldg(c + k));
+            acc = __fadd_rn(acc, __fmul_rn(t, t));
+        }
+        lut[qp * M * ksub + e] = acc;
+    }
+}
+
+template <int G, int DS>
+__global__ void lut_build_scan_kernel(const float* __restrict__ q, long long nq, int D, const float* __restrict__ centroid,
+                                      const float* __restrict__ cb, float* __restrict__ lut_scan) {
+    constexpr int QW = 32 / G, M = 4 * G;
+    extern __shared__ float s_res[];  // [QW][D+4]
+    const int RS = D + 4;
+    const long long qg = blockIdx.x;
+    for (int i = threadIdx.x; i < QW * D; i += blockDim.x) {
+        const int ql = i / D, j = i - ql * D;
+        const long long qi = qg * QW + ql;
+        s_res[ql * RS + j] = qi < nq ? __fsub_rn(q[qi * D + j], centroid[j]) : 0.0f;
+    }
+    __syncthreads();
+    float* out = lut_scan + qg * 32768;
+    for (int e = threadIdx.x; e < 32768; e += blockDim.x) {
+        const int lane = e & 31, msel = (e >> 5) & 1, j = (e >> 6) & 255, pair = e >> 14;
+        const int h = lane / QW, ql = lane - h * QW;
+        const int m = 4 * h + 2 * pair + msel;
+        const float* c = cb + ((long long)m * 256 + j) * DS;
+        const float* r = s_res + ql * RS + m * DS;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DS; k++) {
+            const float t = __fsub_rn(r[k], __ldg(c + k));
+            acc = __fadd_rn(acc, __fmul_rn(t, t));
+        }
+        out[e] = (qg * QW + ql < nq) ? acc : 0.0f;
+    }
+    (void)M;
+}
+
+// =============================================================================================
+// a6 + a7.  THE hot kernel: flat ADC scan with fused exact top-k.
+//
+// Work unit: one CTA = (group of QW = 32/G queries) x (a slice of the coded database).
+// Lane layout inside every warp: lane = h*QW + q, h = lane group owning sub-quantizers
+// 4h..4h+3, q = query within the group.  The CTA keeps the QW queries' LUTs resident in shared
+// memory for its whole life (128 KB, loaded once with TMA bulk copies) laid out so that the
+// word lane l reads always sits in bank l:
+//     byte offset = pair*65536 + code*256 + msel*128 + lane*4      (m = 4h + 2*pair + msel)
+// => every LUT gather instruction is 32 lookups in ONE conflict-free shared-memory wavefront,
+// no matter what the code bytes are (code bytes are warp-uniform per lane group, they only
+// select the row).  The LUT base is 64 KB aligned in the shared window so a single PRMT builds
+// the complete address (byte0 = lane*4, byte1 = code byte, bytes 2-3 = base).
+//
+// A lane only owns 4 of the M sub-quantizers, so the running sum of a row travels through the
+// lane groups like a systolic pipeline: group h adds its 4 entries (in order) to the value
+// received from group h-1 with one warp shuffle, one block (4 rows) later.  The fp32 additions
+// therefore happen in exactly the reference's order m = 0..M-1 starting from 0.0f
+// (IVFOPQ.cpp:302-306) and the scores are bit-identical; the last group owns the final scores.
+//
+// Code bytes stream through a per-warp ring in shared memory filled by 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier); each lane group reads the 32-bit code words of 4 consecutive rows
+// with one 16-byte ld.shared.
+//
+// Top-k: final scores are compared with the query's running threshold; the rare survivors go to
+// a per-warp staging buffer and are merged into the CTA's sorted per-query list (topk.cuh).
+// Each CTA emits k sorted keys per query; topk_merge_kernel merges the slices.
+// =============================================================================================
+template <int G>
+struct ScanCfg {
+    static constexpr int QW = 32 / G;                         // queries per CTA
+    static constexpr int WARPS = 16;
+    static constexpr int STAGE_BLOCKS = (G <= 4) ? 16 : 8;     // blocks (of 4 rows) per ring stage
+    static constexpr int STAGE_ROWS = STAGE_BLOCKS * 4;
+    static constexpr int RING_STAGES = 4;
+    static constexpr int PLANE_RING_BYTES = RING_STAGES * STAGE_ROWS * 4;  // per lane group
+    static constexpr int RING_BYTES = G * PLANE_RING_BYTES;                // per warp
+    static constexpr int SB = (G == 1) ? 8 : 16;               // staging records per (warp, query)
+    static constexpr int STAGING_BYTES = QW * SB * 8;          // per warp
+    static constexpr int LIST_BYTES = QW * KP * 8;
+    static constexpr int LUT_BYTES = 131072;
+    static constexpr int SMEM_BYTES = 232448;                  // 227 KB: one CTA per SM
+};
+
+template <int IMM>
+__device__ __forceinline__ float lds_f32_off(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+
+#define B2_LOOKUP4(S, W)                                                                      \
+    S = __fadd_rn(S, lds_f32_off<0>(__byte_perm(W, basereg, 0x7604)));                          \
+    S = __fadd_rn(S, lds_f32_off<128>(__byte_perm(W, basereg, 0x7614)));                        \
+    S = __fadd_rn(S, lds_f32_off<65536>(__byte_perm(W, basereg, 0x7624)));                      \
+    S = __fadd_rn(S, lds_f32_off<65536 + 128>(__byte_perm(W, basereg, 0x7634)));
+
+template <int G>
+__global__ void __launch_bounds__(ScanCfg<G>::WARPS * 32, 1)
+adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
+                     const float* __restrict__ lut_scan,    // [qgroups][32768]
+                     long long n_rows,                      // valid rows of this shard
+                     long long n_granules,                  // ceil(n_rows / 64)
+                     int n_slices, int k, float clamp, uint32_t id_base,
+                     unsigned long long* __restrict__ out_keys,  // [slice][qgroups*QW][k]
+                     long long q_stride_total,                   // qgroups*QW
+                     int* __restrict__ err_flag) {
+    using C = ScanCfg<G>;
+    constexpr int QW = C::QW;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int h = lane / QW, ql = lane - h * QW;
+    const bool last_group = (h == G - 1);
+    const long long qg = blockIdx.x;
+    const int slice = blockIdx.y;
+
+    // ---- carve shared memory: LUT at a 64 KB aligned window address, the rest around it ----
+    const uint32_t base = smem_u32(dyn_smem);
+    const uint32_t lut = (base + 0xFFFFu) & ~0xFFFFu;
+    uint32_t low_lo = base, low_hi = lut, high_lo = lut + C::LUT_BYTES, high_hi = base + C::SMEM_BYTES;
+    bool ok = true;
+    auto carve = [&](uint32_t bytes) -> uint32_t {
+        uint32_t p;
+        if (low_lo + bytes <= low_hi) { p = low_lo; low_lo += bytes; }
+        else { p = high_lo; high_lo += bytes; if (high_lo > high_hi) ok = false; }
+        return p;
+    };
+    uint32_t ring_w = 0, staging_w = 0;
+    for (int i = 0; i < C::WARPS; i++) { const uint32_t p = carve(C::RING_BYTES); if (i == w) ring_w = p; }
+    const uint32_t lists = carve(C::LIST_BYTES);
+    for (int i = 0; i < C::WARPS; i++) { const uint32_t p = carve(C::STAGING_BYTES); if (i == w) staging_w = p; }
+    const uint32_t misc = carve(1024);
+    if (!ok) { if (threadIdx.x == 0) atomicExch(err_flag, 1); return; }
+    // misc: [0,8) lut barrier | [64, 64+WARPS*32) per-warp full barriers | [640, 640+QW*8) tau keys | [896, 896+QW*4) locks
+    const uint32_t lut_bar = misc;
+    const uint32_t full_bar = misc + 64 + (uint32_t)w * 32;
+    unsigned char* generic_base = dyn_smem - base;  // generic pointer of shared-window address 0
+    volatile unsigned long long* tau_key = (volatile unsigned long long*)(generic_base + misc + 640);
+    int* locks = (int*)(generic_base + misc + 896);
+
+    // ---- this warp's stream of rows ----
+    const long long g_lo = (n_granules * slice) / n_slices, g_hi = (n_granules * (slice + 1)) / n_slices;
+    constexpr int GRAN_PER_STAGE_NUM = C::STAGE_ROWS;  // rows per stage (64 or 32)
+    const long long stages_total = (g_hi - g_lo) * (64 / GRAN_PER_STAGE_NUM);
+    const long long st_per_warp = (stages_total + C::WARPS - 1) / C::WARPS;
+    const long long st_lo = min(stages_total, (long long)w * st_per_warp), st_hi = min(stages_total, st_lo + st_per_warp);
+    const int n_st = (int)(st_hi - st_lo);
+    const long long row0 = g_lo * 64 + st_lo * C::STAGE_ROWS;  // first row of the stream
+    const int nblocks = n_st * C::STAGE_BLOCKS;
+
+    // ---- barriers, lists ----
+    if (threadIdx.x == 0) mbar_init(lut_bar, 1);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < C::RING_STAGES; s++) mbar_init(full_bar + 8 * s, 1);
+    }
+    for (int i = threadIdx.x; i < QW * KP; i += blockDim.x) sts64(lists + (uint32_t)i * 8u, KEY_MAX);
+    if (threadIdx.x < QW) { tau_key[threadIdx.x] = KEY_MAX; locks[threadIdx.x] = 0; }
+    mbar_fence_init();
+    __syncthreads();
+
+    // ---- LUT: 8 TMA bulk copies of 16 KB ----
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(lut_bar, C::LUT_BYTES);
+        const float* src = lut_scan + qg * 32768;
+#pragma unroll
+        for (int i = 0; i < 8; i++) tma_load_1d(lut + i * 16384, src + i * 4096, 16384, lut_bar);
+    }
+
+    // ---- code prefetch ----
+    // stage s of this warp = rows [row0 + s*STAGE_ROWS, +STAGE_ROWS); plane h of it is STAGE_ROWS
+    // consecutive words inside granule (row/64), plane h.
+    auto issue_stage = [&](int s) {
+        const uint32_t bar = full_bar + 8 * (s & (C::RING_STAGES - 1));
+        if (lane == 0) mbar_arrive_expect_tx(bar, G * C::STAGE_ROWS * 4);
+        __syncwarp();
+        if (lane < G) {
+            const long long row = row0 + (long long)s * C::STAGE_ROWS;
+            const long long gran = row >> 6;
+            const int within = (int)(row & 63);
+            const uint32_t* src = codesT + (gran * G + lane) * 64 + within;
+            const uint32_t dst = ring_w + (uint32_t)lane * C::PLANE_RING_BYTES +
+                                 (uint32_t)(s & (C::RING_STAGES - 1)) * (C::STAGE_ROWS * 4);
+            tma_load_1d(dst, src, C::STAGE_ROWS * 4, bar);
+        }
+    };
+    if (n_st > 0) issue_stage(0);
+    if (n_st > 1) issue_stage(1);
+
+    mbar_wait(lut_bar, 0);  // LUT resident
+
+    const uint32_t basereg = lut + (uint32_t)lane * 4u;
+    const uint32_t plane = ring_w + (uint32_t)h * C::PLANE_RING_BYTES;
+    const uint32_t my_staging = staging_w + (uint32_t)ql * (C::SB * 8);
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    // tau = prefilter threshold on the RAW score: the k-th best distance, or +inf while the list
+    // is not full or while the clamp value itself would still qualify (clamped scores tie at
+    // `clamp`, the record comparison below then decides).  -inf on lanes that own no final score.
+    unsigned long long tkey = KEY_MAX;
+    float tau = last_group ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+    int cnt = 0;  // staged records (last group lanes)
+    auto refresh_tau = [&]() {
+        if (last_group) {
+            tkey = tau_key[ql];
+            const float t = tau_f32_of(tkey);
+            tau = (clamp <= t) ? __int_as_float(0x7f800000) : t;
+        }
+    };
+    // byte offset of this lane's current block inside its plane ring (block index = Bg - h)
+    uint32_t coff = (uint32_t)((-h * 16) & (C::PLANE_RING_BYTES - 1));
+
+    auto rare_path = [&](int Bg) {
+        // Bg = block counter of lane group 0; this lane's block is Bg - h.
+        const int Bh = Bg - h;
+        if (last_group && Bh >= 0 && Bh < nblocks) {
+            const long long r = row0 + (long long)Bh * 4;
+            const float sc[4] = {o0, o1, o2, o3};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float s = sc[j];
+                s = clamp < s ? clamp : s;  // std::min(score, threhold-initialised slot), IVFOPQ.cpp:410
+                const unsigned long long key = make_key(f32_orderable(s), id_base + (uint32_t)(r + j));
+                if (key < tkey && r + j < n_rows) {
+                    sts64(my_staging + (uint32_t)cnt * 8u, key);
+                    cnt++;
+                }
+            }
+        }
+        __syncwarp();
+        unsigned need = __ballot_sync(0xffffffffu, cnt > C::SB - 4);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int qsel = src - (G - 1) * QW;
+            const int nb = __shfl_sync(0xffffffffu, cnt, src);
+            warp_flush(lists + (uint32_t)qsel * (KP * 8), locks + qsel, tau_key + qsel,
+                       staging_w + (uint32_t)qsel * (C::SB * 8), nb, k);
+            if (lane == src) cnt = 0;
+        }
+        refresh_tau();
+    };
+
+    auto block_body = [&](int Bg) {
+        const uint4 cw = lds128(plane + coff);
+        coff = (coff + 16u) & (uint32_t)(C::PLANE_RING_BYTES - 1);
+        float s0, s1, s2, s3;
+        if (G > 1) {
+            s0 = __shfl_up_sync(0xffffffffu, o0, QW);
+            s1 = __shfl_up_sync(0xffffffffu, o1, QW);
+            s2 = __shfl_up_sync(0xffffffffu, o2, QW);
+            s3 = __shfl_up_sync(0xffffffffu, o3, QW);
+            if (h == 0) { s0 = 0.f; s1 = 0.f; s2 = 0.f; s3 = 0.f; }
+        } else {
+            s0 = 0.f; s1 = 0.f; s2 = 0.f; s3 = 0.f;
+        }
+        B2_LOOKUP4(s0, cw.x)
+        B2_LOOKUP4(s1, cw.y)
+        B2_LOOKUP4(s2, cw.z)
+        B2_LOOKUP4(s3, cw.w)
+        o0 = s0; o1 = s1; o2 = s2; o3 = s3;
+        const float mn = fminf(fminf(s0, s1), fminf(s2, s3));
+        if (__any_sync(0xffffffffu, mn <= tau)) rare_path(Bg);
+    };
+
+    int Bg = 0;
+    for (int st = 0; st < n_st; st++) {
+        if (st + 2 < n_st) issue_stage(st + 2);
+        mbar_wait(full_bar + 8 * (st & (C::RING_STAGES - 1)), (uint32_t)(st / C::RING_STAGES) & 1u);
+        refresh_tau();
+#pragma unroll 4
+        for (int bb = 0; bb < C::STAGE_BLOCKS; bb++, Bg++) block_body(Bg);
+    }
+    for (int d = 0; d < G - 1; d++, Bg++) block_body(Bg);  // drain the lane-group pipeline
+
+    // ---- flush what is still staged, then emit the CTA's sorted lists ----
+    {
+        unsigned need = __ballot_sync(0xffffffffu, last_group && cnt > 0);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int qsel = src - (G - 1) * QW;
+            const int nb = __shfl_sync(0xffffffffu, cnt, src);
+            warp_flush(lists + (uint32_t)qsel * (KP * 8), locks + qsel, tau_key + qsel,
+                       staging_w + (uint32_t)qsel * (C::SB * 8), nb, k);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < QW * k; i += blockDim.x) {
+        const int qq = i / k, j = i - qq * k;
+        out_keys[((long long)slice * q_stride_total + qg * QW + qq) * k + j] = lds64(lists + (uint32_t)(qq * KP + j) * 8u);
+    }
+}
+
+// =============================================================================================
+// Generic IVF scan (true list probing, any K): one CTA per (query, probe).  The LUT for the
+// probed list lives in shared memory, lanes take rows of the list.  Two outputs:
+//   group mode: match[q][group] = min(score, match)   (IVFOPQ::QueryThrehold, IVFOPQ.cpp:403-411)
+//   row mode  : scores[q][row]  = min(score, clamp-initialised slot)   (videoId = row)
+// Scores are non-negative, so an integer atomicMin on the float bits is an exact float min.
+// =============================================================================================
+__global__ void ivf_scan_kernel(const float* __restrict__ lut,            // [nq*nprobe][M*ksub]
+                                const int* __restrict__ probes,           // [nq*nprobe]
+                                const long long* __restrict__ list_off,   // [K+1] CSR offsets (sorted order)
+                                const unsigned char* __restrict__ codes_sorted,  // [n][M]
+                                const int* __restrict__ slot_sorted,      // [n] group id or original row
+                                int M, int ksub, int nprobe, long long out_stride, float* __restrict__ out) {
+    extern __shared__ float s_lut[];
+    const long long qp = blockIdx.x;
+    const long long qi = qp / nprobe;
+    const int vw = probes[qp];
+    for (int e = threadIdx.x; e < M * ksub; e += blockDim.x) s_lut[e] = lut[qp * M * ksub + e];
+    __syncthreads();
+    const long long lo = list_off[vw], hi = list_off[vw + 1];
+    int* o = (int*)(out + qi * out_stride);
+    for (long long r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+        const unsigned char* c = codes_sorted + r * M;
+        float score = 0.0f;
+        for (int m = 0; m < M; m++) score = __fadd_rn(score, s_lut[m * ksub + c[m]]);
+        atomicMin(o + slot_sorted[r], __float_as_int(score));
+    }
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// =============================================================================================
+// Dense select (get_sort_results, opq/src/common.h:25-37): k smallest (score, id) of a dense
+// score row.  One CTA per query, warps stride over the row, ballot-compacted staging.
+// =============================================================================================
+__global__ void dense_select_topk_kernel(const float* __restrict__ scores, long long n, long long stride, int k,
+                                         uint32_t id_base, unsigned long long* __restrict__ out_keys) {
+    constexpr int SBW = 64;
+    __shared__ __align__(16) unsigned long long s_list[KP];
+    __shared__ __align__(16) unsigned long long s_stage[8][SBW];
+    __shared__ unsigned long long s_tau;
+    __shared__ int s_lock;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long q = blockIdx.x;
+    for (int i = threadIdx.x; i < KP; i += blockDim.x) s_list[i] = KEY_MAX;
+    if (threadIdx.x == 0) { s_tau = KEY_MAX; s_lock = 0; }
+    __syncthreads();
+    const uint32_t L = smem_u32(s_list), ST = smem_u32(&s_stage[w][0]);
+    volatile unsigned long long* tau_p = &s_tau;
+    int cnt = 0;
+    const float* row = scores + q * stride;
+    auto flush_all = [&]() {
+        for (int off = 0; off < cnt; off += 32)
+            warp_flush(L, &s_lock, tau_p, ST + off * 8, min(32, cnt - off), k);
+        cnt = 0;
+    };
+    for (long long i0 = (long long)w * 32; i0 < n; i0 += (long long)nw * 32) {
+        const long long i = i0 + lane;
+        const unsigned long long tkey = *tau_p;
+        bool pass = false;
+        unsigned long long key = 0;
+        if (i < n) { key = make_key(f32_orderable(row[i]), id_base + (uint32_t)i); pass = key < tkey; }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            if (pass) sts64(ST + (uint32_t)(cnt + __popc(m & ((1u << lane) - 1))) * 8u, key);
+            cnt += __popc(m);
+            __syncwarp();
+            if (cnt > SBW - 32) flush_all();
+        }
+    }
+    flush_all();
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) out_keys[q * k + j] = s_list[j];
+}
+
+// =============================================================================================
+// host launchers
+// =============================================================================================
+static inline unsigned grid_for(long long work, int per_block, int sm_count, int waves = 8) {
+    long long g = (work + per_block - 1) / per_block;
+    const long long cap = (long long)sm_count * waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+int launch_rotate_perm(Ctx* ctx, const float* x, long long n, int D, const int* perm, float* y) {
+    if (n == 0) return 0;
+    rotate_perm_kernel<<<grid_for(n * D, 256, ctx->sm_count), 256, 0, ctx->stream>>>(x, n, D, perm, y);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_coarse_assign(Ctx* ctx, const float* x, long long n, int D, const float* coarseT, int K, int* out_list) {
+    if (n == 0) return 0;
+    const int warps = 8;
+    coarse_assign_kernel<<<grid_for(n, warps, ctx->sm_count), warps * 32, warps * D * sizeof(float), ctx->stream>>>(
+        x, n, D, coarseT, K, out_list);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_pq_encode(Ctx* ctx, const float* x, long long n, int D, const float* coarse, const int* list, const float* cbT,
+                     int M, int ksub, unsigned char* codes) {
+    if (n == 0) return 0;
+    const int ds = D / M;
+    const unsigned grid = grid_for(n * M, 8, ctx->sm_count, 16);
+#define B2_ENC(DS_)                                                                                              \
+    case DS_:                                                                                                    \
+        pq_encode_kernel<DS_><<<grid, 256, 0, ctx->stream>>>(x, n, D, coarse, list, cbT, M, ksub, codes);        \
+        break;
+    switch (ds) {
+        B2_ENC(1) B2_ENC(2) B2_ENC(4) B2_ENC(8) B2_ENC(16) B2_ENC(32)
+        default: B2_FAIL(-4, "pq_encode: unsupported sub-vector dimension (D/M must be 1,2,4,8,16,32)");
+    }
+#undef B2_ENC
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_codes_to_scan_layout(Ctx* ctx, const unsigned char* codes, long long n, int M, uint32_t* codesT, long long n_pad) {
+    if (n_pad == 0) return 0;
+    codes_to_scan_layout_kernel<<<grid_for(n_pad * (M / 4), 256, ctx->sm_count), 256, 0, ctx->stream>>>(codes, n, M, codesT, n_pad);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_coarse_probe(Ctx* ctx, const float* q, long long nq, int D, const float* coarseT, int K, int nk, int* out_lists) {
+    if (nq == 0) return 0;
+    if (nk > 8 || nk < 1 || nk > K) B2_FAIL(-1, "coarse_probe: nprobe must be in [1, min(8, K)]");
+    const int warps = 4;
+    coarse_probe_kernel<<<grid_for(nq, warps, ctx->sm_count), warps * 32, warps * D * sizeof(float), ctx->stream>>>(
+        q, nq, D, coarseT, K, nk, out_lists);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_lut_build_std(Ctx* ctx, const float* q, long long nq, int D, const int* probes, int nprobe, const float* coarse,
+                         const float* cb, int M, int ksub, float* lut) {
+    if (nq == 0) return 0;
+    const int ds = D / M;
+    const unsigned grid = (unsigned)(nq * nprobe);
+#define B2_LUT(DS_)                                                                                             \
+    case DS_:                                                                                                   \
+        lut_build_std_kernel<DS_><<<grid, 256, D * sizeof(float), ctx->stream>>>(q, nq, D, probes, nprobe, coarse, cb, \
+                                                                                 M, ksub, lut);                  \
+        break;
+    switch (ds) {
+        B2_LUT(1) B2_LUT(2) B2_LUT(4) B2_LUT(8) B2_LUT(16) B2_LUT(32)
+        default: B2_FAIL(-4, "lut_build: unsupported sub-vector dimension");
+    }
+#undef B2_LUT
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int G>
+static int lut_scan_dispatch(Ctx* ctx, const float* q, long long nq, int D, const float* centroid, const float* cb,
+                             float* lut_scan) {
+    constexpr int QW = 32 / G, M = 4 * G;
+    const int ds = D / M;
+    const unsigned grid = (unsigned)((nq + QW - 1) / QW);
+    const size_t smem = (size_t)QW * (D + 4) * sizeof(float);
+#define B2_LS(DS_)                                                                                                  \
+    case DS_:                                                                                                       \
+        if (smem > 48 * 1024)                                                                                       \
+            cudaFuncSetAttribute(lut_build_scan_kernel<G, DS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        lut_build_scan_kernel<G, DS_><<<grid, 512, smem, ctx->stream>>>(q, nq, D, centroid, cb, lut_scan);           \
+        break;
+    switch (ds) {
+        B2_LS(1) B2_LS(2) B2_LS(4) B2_LS(8) B2_LS(16) B2_LS(32)
+        default: B2_FAIL(-4, "lut_build_scan: unsupported sub-vector dimension");
+    }
+#undef B2_LS
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_lut_build_scan(Ctx* ctx, int M, const float* q, long long nq, int D, const float* centroid, const float* cb,
+                          float* lut_scan) {
+    if (nq == 0) return 0;
+    switch (M) {
+        case 4: return lut_scan_dispatch<1>(ctx, q, nq, D, centroid, cb, lut_scan);
+        case 8: return lut_scan_dispatch<2>(ctx, q, nq, D, centroid, cb, lut_scan);
+        case 16: return lut_scan_dispatch<4>(ctx, q, nq, D, centroid, cb, lut_scan);
+        case 32: return lut_scan_dispatch<8>(ctx, q, nq, D, centroid, cb, lut_scan);
+        default: B2_FAIL(-4, "fast ADC scan supports M in {4, 8, 16, 32}");
+    }
+}
+
+int scan_queries_per_cta(int M) { return M >= 4 ? 128 / M : 0; }
+
+// number of database slices: fill whole waves of one-CTA-per-SM, keep slices long
+int scan_pick_slices(int sm_count, long long qgroups, long long n_granules) {
+    if (qgroups <= 0) return 1;
+    int best_s = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 64; s++) {
+        if (s > 1 && n_granules / s < 64) break;  // >= 4096 rows per CTA
+        const double ctas = (double)qgroups * s;
+        const double waves = ctas / sm_count;
+        const double eff = waves / (double)(long long)(waves + 0.999999);
+        if (eff > best_eff + 0.02) { best_eff = eff; best_s = s; }
+        if (best_eff > 0.97) break;
+    }
+    return best_s;
+}
+
+template <int G>
+static int scan_dispatch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
+                         int n_slices, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
+    using C = ScanCfg<G>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const long long n_gran = (n_rows + 63) / 64;
+    dim3 grid((unsigned)qgroups, (unsigned)n_slices);
+    adc_scan_topk_kernel<G><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
+        codesT, lut_scan, n_rows, n_gran, n_slices, k, clamp, id_base, out_keys, qgroups * C::QW, ctx->d_err);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_adc_scan_topk(Ctx* ctx, int M, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
+                         int n_slices, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
+    if (k < 1 || k > KP) B2_FAIL(-4, "fused ADC top-k supports 1 <= k <= 128");
+    switch (M) {
+        case 4: return scan_dispatch<1>(ctx, codesT, lut_scan, n_rows, qgroups, n_slices, k, clamp, id_base, out_keys);
+        case 8: return scan_dispatch<2>(ctx, codesT, lut_scan, n_rows, qgroups, n_slices, k, clamp, id_base, out_keys);
+        case 16: return scan_dispatch<4>(ctx, codesT, lut_scan, n_rows, qgroups, n_slices, k, clamp, id_base, out_keys);
+        case 32: return scan_dispatch<8>(ctx, codesT, lut_scan, n_rows, qgroups, n_slices, k, clamp, id_base, out_keys);
+        default: B2_FAIL(-4, "fast ADC scan supports M in {4, 8, 16, 32}");
+    }
+}
+
+int launch_fill_f32(Ctx* ctx, float* p, long long n, float v) {
+    if (n == 0) return 0;
+    fill_f32_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(p, n, v);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_ivf_scan(Ctx* ctx, const float* lut, const int* probes, const long long* list_off, const unsigned char* codes_sorted,
+                    const int* slot_sorted, int M, int ksub, long long nq, int nprobe, long long out_stride, float* out) {
+    if (nq == 0) return 0;
+    const size_t smem = (size_t)M * ksub * sizeof(float);
+    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(ivf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ivf_scan_kernel<<<(unsigned)(nq * nprobe), 256, smem, ctx->stream>>>(lut, probes, list_off, codes_sorted, slot_sorted, M,
+                                                                         ksub, nprobe, out_stride, out);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_dense_select_topk(Ctx* ctx, const float* scores, long long nq, long long n, long long stride, int k,
+                             uint32_t id_base, unsigned long long* out_keys) {
+    if (nq == 0) return 0;
+    if (k < 1 || k > KP) B2_FAIL(-4, "dense select supports 1 <= k <= 128");
+    dense_select_topk_kernel<<<(unsigned)nq, 256, 0, ctx->stream>>>(scores, n, stride, k, id_base, out_keys);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200nn

@@ -1,0 +1,27 @@
+// pq_kernels.cuh -- launchers of the (O)PQ kernels (definitions in pq_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200nn {
+
+int launch_rotate_perm(Ctx* ctx, const float* x, long long n, int D, const int* perm, float* y);
+int launch_coarse_assign(Ctx* ctx, const float* x, long long n, int D, const float* coarseT, int K, int* out_list);
+int launch_pq_encode(Ctx* ctx, const float* x, long long n, int D, const float* coarse, const int* list, const float* cbT,
+                     int M, int ksub, unsigned char* codes);
+int launch_codes_to_scan_layout(Ctx* ctx, const unsigned char* codes, long long n, int M, uint32_t* codesT, long long n_pad);
+int launch_coarse_probe(Ctx* ctx, const float* q, long long nq, int D, const float* coarseT, int K, int nk, int* out_lists);
+int launch_lut_build_std(Ctx* ctx, const float* q, long long nq, int D, const int* probes, int nprobe, const float* coarse,
+                         const float* cb, int M, int ksub, float* lut);
+int launch_lut_build_scan(Ctx* ctx, int M, const float* q, long long nq, int D, const float* centroid, const float* cb,
+                          float* lut_scan);
+int scan_queries_per_cta(int M);
+int scan_pick_slices(int sm_count, long long qgroups, long long n_granules);
+int launch_adc_scan_topk(Ctx* ctx, int M, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
+                         int n_slices, int k, float clamp, uint32_t id_base, unsigned long long* out_keys);
+int launch_fill_f32(Ctx* ctx, float* p, long long n, float v);
+int launch_ivf_scan(Ctx* ctx, const float* lut, const int* probes, const long long* list_off, const unsigned char* codes_sorted,
+                    const int* slot_sorted, int M, int ksub, long long nq, int nprobe, long long out_stride, float* out);
+int launch_dense_select_topk(Ctx* ctx, const float* scores, long long nq, long long n, long long stride, int k,
+                             uint32_t id_base, unsigned long long* out_keys);
+
+}  // namespace b200nn

@@ -1,0 +1,68 @@
+// topk_merge.cu -- cross-slice / cross-shard merge of sorted top-k key lists.
+#include "topk.cuh"
+
+namespace b200nn {
+
+// ---------------------------------------------------------------------------------------------
+// Merge of L sorted key lists per query (slices of one GPU, or the all-gathered shard results).
+// One warp per query; rank = own index + sum over the other lists of lower_bound(key).
+// keys[(l * list_stride) + q * k + j].  Missing results (fewer than k real records) are written
+// as (+inf | INT32_MAX, UINT64_MAX).
+// ---------------------------------------------------------------------------------------------
+__global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, int L, long long nq, int k,
+                                  long long list_stride, float* __restrict__ out_dist_f, int* __restrict__ out_dist_i,
+                                  unsigned long long* __restrict__ out_id, unsigned long long* __restrict__ out_key) {
+    const int lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const unsigned long long* base = keys + q * k;
+    int real = 0;
+    for (int e = lane; e < L * k; e += 32) {
+        const int l = e / k, j = e - l * k;
+        const unsigned long long key = base[(long long)l * list_stride + j];
+        if (key == KEY_MAX) continue;
+        real++;
+        int rank = j;
+        for (int l2 = 0; l2 < L; l2++) {
+            if (l2 == l) continue;
+            const unsigned long long* o = base + (long long)l2 * list_stride;
+            int lo = 0, hi = k;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (o[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            const long long o = q * k + rank;
+            const uint32_t ord = (uint32_t)(key >> 32);
+            if (out_dist_f) out_dist_f[o] = f32_from_orderable(ord);
+            if (out_dist_i) out_dist_i[o] = s32_from_orderable(ord);
+            if (out_id) out_id[o] = key & 0xFFFFFFFFull;
+            if (out_key) out_key[o] = key;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) real += __shfl_xor_sync(0xffffffffu, real, s);
+    for (int r = real + lane; r < k; r += 32) {
+        const long long o = q * k + r;
+        if (out_dist_f) out_dist_f[o] = __int_as_float(0x7f800000);
+        if (out_dist_i) out_dist_i[o] = 0x7fffffff;
+        if (out_id) out_id[o] = 0xFFFFFFFFFFFFFFFFull;
+        if (out_key) out_key[o] = KEY_MAX;
+    }
+}
+
+
+int launch_topk_merge(Ctx* ctx, const unsigned long long* keys, int L, long long nq, int k, long long list_stride,
+                      float* out_dist_f, int* out_dist_i, unsigned long long* out_id, unsigned long long* out_key) {
+    if (nq <= 0) return 0;
+    const int warps = 4;
+    topk_merge_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, 0, ctx->stream>>>(
+        keys, L, nq, k, list_stride, out_dist_f, out_dist_i, out_id, out_key);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200nn

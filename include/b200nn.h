@@ -1,0 +1,141 @@
+/*
+ * b200nn.h -- C ABI of the B200-native quantized nearest-neighbour path (drop-in boundary).
+ *
+ * Each entry point replaces one reference interface (paths relative to willard-yuan/cvt):
+ *   flat  : hnswlib::BruteforceSearch<dist_t>::addPoint/searchKnn/saveIndex/loadIndex
+ *           brute_force_search/src/brutoforce.hpp:43-56,73-93,95-134 with the distance functions of
+ *           space_ip.hpp:25-207 and hnsw_sifts_retrieval/hnswlib/space_l2.h:26-245
+ *   pq    : IVFOPQ::LoadModel/Add/IndexDatabase/Query/QueryThrehold/SaveIndex
+ *           opq/src/IVFOPQ.h:31-47, opq/src/IVFOPQ.cpp:64-583, get_sort_results opq/src/common.h:25-37
+ *   sq    : cvtk::quant::Int8Quan::Int8Encode/Int8Decode/L2NormalizeVector
+ *           scalar_quantization/scalar_quantization/int8_quan.h:17-37, int8_quan.cc:46-132
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0 on success,
+ * <0 on error (message via b200nn_last_error(), thread-local).  Pointers are HOST pointers unless
+ * the name ends in _dev (device pointers on the context's GPU; work is enqueued on the context
+ * stream and NOT synchronised -- call b200nn_ctx_synchronize or sync the stream you supplied).
+ * There is no CPU fallback: without a CUDA device ctx_create fails.
+ */
+#ifndef B200NN_H
+#define B200NN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NN_OK 0
+#define B200NN_ERR_INVALID -1   /* bad argument */
+#define B200NN_ERR_CUDA -2      /* CUDA runtime / launch failure */
+#define B200NN_ERR_IO -3        /* file format / open failure */
+#define B200NN_ERR_UNSUPPORTED -4
+#define B200NN_ERR_STATE -5     /* e.g. capacity exceeded, duplicate label */
+
+typedef struct b200nn_ctx* b200nn_ctx_t;
+typedef struct b200nn_flat* b200nn_flat_t;
+typedef struct b200nn_pq* b200nn_pq_t;
+typedef struct b200nn_sq* b200nn_sq_t;
+
+/* ---- context ---------------------------------------------------------------------------- */
+const char* b200nn_last_error(void);
+const char* b200nn_version(void);
+int b200nn_ctx_create(int device, b200nn_ctx_t* out);
+void b200nn_ctx_destroy(b200nn_ctx_t ctx);
+/* Adopt an external cudaStream_t (e.g. torch's current stream); NULL restores the private stream. */
+int b200nn_ctx_set_stream(b200nn_ctx_t ctx, void* cuda_stream);
+int b200nn_ctx_synchronize(b200nn_ctx_t ctx);
+/* Number of kernels this library has launched through ctx so far (bench.py's gpu_launches). */
+int b200nn_ctx_launch_count(b200nn_ctx_t ctx, uint64_t* out);
+/* CUDA-event timing on the context stream: mark(slot) records an event, elapsed returns ms. */
+int b200nn_ctx_event_record(b200nn_ctx_t ctx, int slot);
+int b200nn_ctx_event_elapsed_ms(b200nn_ctx_t ctx, int slot_a, int slot_b, float* ms);
+
+/* ---- flat exact index: BruteforceSearch<float|int> drop-in ---------------------------------
+ * metric: 0 = 1 - <a,b>   (InnerProductSpace, space_ip.hpp)        elements f32, dist f32
+ *         1 = sum (a-b)^2 (L2Space, space_l2.h:26-180)             elements f32, dist f32
+ *         2 = sum (a-b)^2 (L2SpaceI, space_l2.h:186-245)           elements u8,  dist s32
+ * order : accumulation order of the reference's SIMD kernels (bit-exact fp32 distances):
+ *         1 = scalar loop, 4 = SSE (the brute-force CLI's own build flags), 8 = AVX (dim%16==0).
+ * Result set = the k smallest under lexicographic (dist, label), ascending -- the order
+ * brutoforce.hpp:73-93 yields once its max-heap is drained and reversed (brute_force.cpp:89-101). */
+#define B200NN_METRIC_IP 0
+#define B200NN_METRIC_L2 1
+#define B200NN_METRIC_L2_U8 2
+int b200nn_flat_create(b200nn_ctx_t ctx, int metric, int order, size_t dim, size_t max_elements, b200nn_flat_t* out);
+void b200nn_flat_destroy(b200nn_flat_t idx);
+/* addPoint for n rows; duplicate label -> ERR_STATE "Ids have to be unique"; capacity -> ERR_STATE. */
+int b200nn_flat_add(b200nn_flat_t idx, const void* vectors, const uint64_t* labels, size_t n);
+int b200nn_flat_remove(b200nn_flat_t idx, uint64_t label); /* removePoint: last row moves into the hole */
+int b200nn_flat_size(b200nn_flat_t idx, size_t* out);
+/* searchKnn for nq queries.  out_dist is f32 (metric 0,1) or s32 (metric 2), [nq,k]; out_label [nq,k].
+ * If fewer than k rows are indexed the tail is filled with +inf / INT32_MAX and label UINT64_MAX
+ * (the reference reads uninitialised memory there). */
+int b200nn_flat_search(b200nn_flat_t idx, const void* queries, size_t nq, size_t k, void* out_dist, uint64_t* out_label);
+int b200nn_flat_search_dev(b200nn_flat_t idx, const void* queries_dev, size_t nq, size_t k, void* out_dist_dev,
+                           uint64_t* out_label_dev);
+int b200nn_flat_save(b200nn_flat_t idx, const char* path);  /* byte format of brutoforce.hpp:95-106 */
+int b200nn_flat_load(b200nn_ctx_t ctx, int metric, int order, size_t dim, const char* path, b200nn_flat_t* out);
+
+/* ---- (O)PQ / IVFOPQ ----------------------------------------------------------------------
+ * Model = D, K coarse centroids, M sub-quantizers x ksub(=256) codewords, and the "rotation":
+ * a permutation perm[D] (y[i] = x[perm[i]], IVFOPQ::reorder, IVFOPQ.cpp:424-439) and/or a dense
+ * row-major R[D,D] (y = R x, tcgen05 split-TF32 GEMM).  clamp_threshold is the reference's
+ * `threhold = 1.0` (IVFOPQ.cpp:5,262,308); pass INFINITY to disable it. */
+int b200nn_pq_create(b200nn_ctx_t ctx, int D, int K, int M, int ksub, const float* coarse, const float* codebooks,
+                     const int32_t* perm, const float* R, float clamp_threshold, b200nn_pq_t* out);
+int b200nn_pq_load_model(b200nn_ctx_t ctx, const char* model_path, b200nn_pq_t* out); /* IVFOPQ::LoadModel format */
+void b200nn_pq_destroy(b200nn_pq_t idx);
+int b200nn_pq_set_clamp(b200nn_pq_t idx, float clamp_threshold);
+int b200nn_pq_info(b200nn_pq_t idx, int* D, int* K, int* M, int* ksub, uint64_t* n_rows, uint64_t* n_groups);
+/* a1: rotation of n raw rows. */
+int b200nn_pq_rotate(b200nn_pq_t idx, const float* x, size_t n, float* y);
+/* a2+a3: coarse argmin + residual PQ argmin of already-rotated rows (IVFOPQ::Add, :105-174). */
+int b200nn_pq_encode(b200nn_pq_t idx, const float* x_rotated, size_t n, int32_t* out_list, uint8_t* out_codes);
+/* rotate + encode + append.  group_ids = videoId per row (NULL: one new group per row, id = row). */
+int b200nn_pq_add(b200nn_pq_t idx, const float* x_raw, size_t n, const int32_t* group_ids);
+int b200nn_pq_add_dev(b200nn_pq_t idx, const float* x_raw_dev, size_t n, const int32_t* group_ids_dev);
+/* read back what Add stored, rows [start, start+n) in insertion order. */
+int b200nn_pq_get_rows(b200nn_pq_t idx, uint64_t start, size_t n, int32_t* out_list, int32_t* out_group,
+                       uint8_t* out_codes);
+/* a4+a5: coarse top-nprobe (in the reference's pop order) + residual LUTs [nq,nprobe,M,ksub]. */
+int b200nn_pq_build_lut(b200nn_pq_t idx, const float* q_rotated, size_t nq, int nprobe, int32_t* out_lists,
+                        float* out_lut);
+/* IVFOPQ::QueryThrehold: out_scores [nq, n_groups], clamp-initialised, min-aggregated per group. */
+int b200nn_pq_scores(b200nn_pq_t idx, const float* q_raw, size_t nq, int nprobe, float* out_scores);
+/* a1,a4,a5,a6,a7 fused: per-row ADC scores (clamped) -> k smallest under (score,row), ascending.
+ * out_id = id_base + row index.  K==1 runs the TMA-staged conflict-free scan kernel. */
+int b200nn_pq_search(b200nn_pq_t idx, const float* q_raw, size_t nq, int nprobe, size_t k, float* out_dist,
+                     uint64_t* out_id);
+/* device variant.  out_key_dev (may be NULL) additionally receives the packed sortable keys
+ * ((orderable(score)<<32) | (uint32)(id_base+row)), the record exchanged between shards. */
+int b200nn_pq_search_dev(b200nn_pq_t idx, const float* q_raw_dev, size_t nq, int nprobe, size_t k, float* out_dist_dev,
+                         uint64_t* out_id_dev, uint64_t* out_key_dev, uint64_t id_base);
+/* merge L sorted key lists per query ([L][nq][k] u64, e.g. the all-gathered shard results). */
+int b200nn_topk_merge_dev(b200nn_ctx_t ctx, const uint64_t* keys_dev, int L, size_t nq, size_t k, float* out_dist_dev,
+                          uint64_t* out_id_dev);
+int b200nn_pq_save_index(b200nn_pq_t idx, const char* dir_or_path, const char* const* group_paths); /* App. A-3 */
+int b200nn_pq_load_index(b200nn_ctx_t ctx, const char* path, const int32_t* perm, float clamp, b200nn_pq_t* out);
+/* timing of the last pq_search[_dev] stages in ms: [rotate, lut, scan, merge] (CUDA events). */
+int b200nn_pq_last_timing(b200nn_pq_t idx, float* ms4);
+/* bytes of device memory held by the coded database (codes as scanned). */
+int b200nn_pq_scan_bytes(b200nn_pq_t idx, uint64_t* code_bytes);
+
+/* ---- scalar quantizer: Int8Quan ------------------------------------------------------------ */
+int b200nn_sq_create(b200nn_ctx_t ctx, int d, const float* vmin, const float* vdiff, b200nn_sq_t* out);
+void b200nn_sq_destroy(b200nn_sq_t sq);
+/* faiss RS_minmax (rs_arg = 0) over rows that are ALREADY L2-normalised (sq_train.cpp:84,100-132). */
+int b200nn_sq_train_minmax(b200nn_ctx_t ctx, int d, const float* x, size_t n, float* vmin, float* vdiff);
+/* Int8Encode for n rows (the reference encodes one; n rows = n calls).  l2norm!=0 normalises x IN
+ * PLACE first, exactly as the reference mutates its argument (int8_quan.cc:76-78). */
+int b200nn_sq_encode(b200nn_sq_t sq, float* x, size_t n, int l2norm, uint8_t* codes);
+/* Int8Decode: variant 0 = the reference's double-precision formula (int8_quan.cc:126-130),
+ * variant 1 = faiss 1.5.3's all-float decode (reached via Int8Decode(uint8_t*)/Int8DecodeFaiss). */
+int b200nn_sq_decode(b200nn_sq_t sq, const uint8_t* codes, size_t n, int faiss_float_variant, float* x);
+int b200nn_sq_encode_dev(b200nn_sq_t sq, float* x_dev, size_t n, int l2norm, uint8_t* codes_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NN_H */

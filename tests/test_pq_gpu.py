@@ -1,0 +1,209 @@
+"""GPU parity tests of the (O)PQ path, through the C ABI, against the golden vectors produced by the
+unmodified reference and against the oracle restatement.  Bit-exact: uint8 codes, list ids,
+neighbour ids AND fp32 scores (the kernels reproduce the reference's summation order)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from cvt_b200 import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+G = cases.GOLDEN
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from cvt_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _fixture_files():
+    db = [np.fromfile(os.path.join(G, "opq_fixture", "db", f), dtype="<f4").reshape(-1, 128) for f in cases.FIXTURE_DB]
+    q = [np.fromfile(os.path.join(G, "opq_fixture", "query", f), dtype="<f4").reshape(-1, 128) for f in cases.FIXTURE_QUERY]
+    return db, q
+
+
+def test_shipped_fixture_reduced_model(ctx):
+    """opq/data fixtures + shipped codebooks: IndexDatabase + QueryThrehold."""
+    from cvt_b200 import capi
+    gold = np.load(os.path.join(G, "opq_shipped_k256.npz"))
+    idx = capi.PQIndex.load_model(ctx, os.path.join(G, "opq_shipped_k256.model"))
+    assert (idx.D, idx.K, idx.M, idx.ksub) == (128, 256, 16, 256)
+    db, q = _fixture_files()
+    for gi, rows in enumerate(db):  # one videoId per file, IVFOPQ.cpp:198-201
+        idx.add(rows, np.full(len(rows), gi, dtype=np.int32))
+    assert idx.n_rows == 53 and idx.n_groups == 5
+    lists, groups, codes = idx.get_rows()
+    assert np.array_equal(lists, gold["row_list"])
+    assert np.array_equal(groups, gold["row_group"])
+    assert np.array_equal(codes, gold["codes"])
+    qall = np.concatenate(q)
+    match = idx.scores(qall, nprobe=3)
+    assert np.array_equal(_bits(match), _bits(gold["match"]))
+    # multi_frame_index_test.cpp:56-68: frame-summed scores + get_sort_results, per query file
+    off = 0
+    for fi, rows in enumerate(q):
+        total = np.zeros(5, dtype=np.float32)
+        for f in range(len(rows)):
+            total = total + match[off + f]
+        off += len(rows)
+        s, i = orc.topk_pairs(total, 5)
+        assert np.array_equal(i, gold["file_topk_id"][fi])
+        assert np.array_equal(_bits(s), _bits(gold["file_topk_score"][fi]))
+    idx.close()
+
+    # per-row ids (videoId = row): top-k through the generic IVF path (K = 256, nprobe = 3)
+    idx = capi.PQIndex.load_model(ctx, os.path.join(G, "opq_shipped_k256.model"))
+    idx.add(np.concatenate(db))
+    D, I = idx.search(qall, k=int(gold["pr_topk"]), nprobe=3)
+    assert np.array_equal(I.astype(np.int64), gold["pr_topk_id"])
+    assert np.array_equal(_bits(D), _bits(gold["pr_topk_score"]))
+    idx.close()
+
+
+@pytest.mark.parametrize("name", list(cases.OPQ_CASES))
+def test_opq_synthetic_vs_reference_golden(ctx, name):
+    from cvt_b200 import capi
+    c = cases.opq_case(name)
+    gold = np.load(os.path.join(G, f"opq_{name}.npz"))
+    assert str(gold["input_sha"]) == c["input_sha"]
+    idx = capi.PQIndex.create(ctx, c["coarse"], c["cb"], perm=c["reorder"], clamp=1.0)
+    rpg = c["rows_per_group"]
+    groups = None if rpg == 1 else (np.arange(c["n"]) // rpg).astype(np.int32)
+    idx.add(c["db"], groups)
+    lists, grp, codes = idx.get_rows()
+    assert np.array_equal(lists, gold["row_list"])
+    assert np.array_equal(grp, gold["row_group"])
+    assert np.array_equal(codes, gold["codes"])
+    match = idx.scores(c["q"], nprobe=c["nk"])
+    assert np.array_equal(_bits(match), _bits(gold["match"]))
+    if rpg == 1:
+        D, I = idx.search(c["q"], k=int(gold["topk"]), nprobe=c["nk"])
+        assert np.array_equal(I.astype(np.int64), gold["topk_id"]), name
+        assert np.array_equal(_bits(D), _bits(gold["topk_score"])), name
+    idx.close()
+
+
+def test_rotate_encode_lut_vs_oracle(ctx):
+    from cvt_b200 import capi
+    c = cases.opq_case("ivf_m8")
+    idx = capi.PQIndex.create(ctx, c["coarse"], c["cb"], perm=c["reorder"])
+    xr = idx.rotate(c["db"])
+    assert np.array_equal(_bits(xr), _bits(orc.opq_reorder(c["db"], c["reorder"])))
+    lists, codes = idx.encode(xr)
+    ol = orc.opq_coarse_assign(xr, c["coarse"])
+    assert np.array_equal(lists, ol)
+    assert np.array_equal(codes, orc.opq_pq_encode(xr, c["coarse"], ol, c["cb"]))
+    qr = idx.rotate(c["q"])
+    probes, lut = idx.build_lut(qr, nprobe=3)
+    for i in range(len(qr)):
+        op = orc.opq_coarse_probe(qr[i], c["coarse"], 3)
+        assert np.array_equal(probes[i], op)
+        for p in range(3):
+            assert np.array_equal(_bits(lut[i, p]), _bits(orc.opq_build_lut(qr[i], c["coarse"][op[p]], c["cb"])))
+    idx.close()
+
+
+def _random_flat_index(ctx, n, D, M, seed, clamp=np.inf):
+    from cvt_b200 import capi
+    rng = np.random.Generator(np.random.PCG64(seed))
+    db = synth.sift_like(n, D, seed=seed)
+    perm = synth.SHIPPED_REORDER_128 if D == 128 else synth.random_permutation(D, seed)
+    coarse, cb = synth.train_pq_model(db[:2000][:, perm], M, 256, 1, iters=2, seed=seed + 1, train_rows=2000)
+    coarse = (rng.standard_normal((1, D)) * 0.01).astype(np.float32)
+    idx = capi.PQIndex.create(ctx, coarse, cb, perm=perm, clamp=clamp)
+    idx.add(db)
+    return idx, db, perm, coarse, cb
+
+
+@pytest.mark.parametrize("M,n,nq,k", [(16, 100_003, 67, 100), (8, 20_000, 19, 10), (32, 30_011, 21, 128), (4, 5_000, 40, 1),
+                                       (16, 50, 9, 100), (16, 4097, 8, 7)])
+def test_fast_scan_vs_oracle_and_generic(ctx, M, n, nq, k):
+    """TMA-staged conflict-free scan == oracle restatement (ids and score bits), including ragged
+    sizes (n % 64 != 0, nq % queries-per-CTA != 0, n < k) and every supported M."""
+    D = 128
+    idx, db, perm, coarse, cb = _random_flat_index(ctx, n, D, M, seed=1000 + M + n)
+    q = synth.sift_like(nq, D, seed=77 + M)
+    Dg, Ig = idx.search(q, k=k, nprobe=1)
+    _, _, codes = idx.get_rows()
+    xr = orc.opq_reorder(db, perm)
+    assert np.array_equal(codes, orc.opq_pq_encode(xr, coarse, np.zeros(n, np.int32), cb))
+    qr = orc.opq_reorder(q, perm)
+    check = range(nq) if n <= 30_000 else range(0, nq, 8)
+    for i in check:
+        lut = orc.opq_build_lut(qr[i], coarse[0], cb)
+        s = orc.opq_adc_scan(lut, codes)
+        os_, oi = orc.topk_pairs(s, k)
+        kk = min(k, n)
+        assert np.array_equal(Ig[i, :kk].astype(np.int64), oi[:kk]), (M, n, i)
+        assert np.array_equal(_bits(Dg[i, :kk]), _bits(os_[:kk])), (M, n, i)
+        if kk < k:
+            assert np.all(np.isinf(Dg[i, kk:])) and np.all(Ig[i, kk:] == np.uint64(0xFFFFFFFFFFFFFFFF))
+    idx.close()
+
+
+def test_clamp_ties_fast_scan(ctx):
+    """threhold = 1.0 (IVFOPQ.cpp:5): scores >= 1 collapse to exactly 1.0 and ids break the ties."""
+    n, D, M, k = 3000, 128, 16, 64
+    idx, db, perm, coarse, cb = _random_flat_index(ctx, n, D, M, seed=4242, clamp=1.0)
+    q = synth.sift_like(12, D, seed=5) * np.float32(2.0)
+    Dg, Ig = idx.search(q, k=k, nprobe=1)
+    _, _, codes = idx.get_rows()
+    qr = orc.opq_reorder(q, perm)
+    ntie = 0
+    for i in range(len(q)):
+        s = np.minimum(orc.opq_adc_scan(orc.opq_build_lut(qr[i], coarse[0], cb), codes), np.float32(1.0))
+        os_, oi = orc.topk_pairs(s, k)
+        assert np.array_equal(Ig[i].astype(np.int64), oi)
+        assert np.array_equal(_bits(Dg[i]), _bits(os_))
+        ntie += int((os_ == 1.0).sum())
+    assert ntie > 0, "the case must exercise clamp ties"
+    idx.close()
+
+
+def test_empty_and_errors(ctx):
+    from cvt_b200 import capi
+    c = cases.opq_case("flat_m16")
+    idx = capi.PQIndex.create(ctx, c["coarse"], c["cb"], perm=c["reorder"])
+    D, I = idx.search(c["q"][:3], k=5)
+    assert np.all(np.isinf(D)) and np.all(I == np.uint64(0xFFFFFFFFFFFFFFFF))
+    with pytest.raises(capi.B200nnError):
+        idx.search(c["q"][:3], k=129)
+    with pytest.raises(capi.B200nnError):
+        idx.search(c["q"][:3], k=5, nprobe=2)  # K == 1
+    with pytest.raises(capi.B200nnError):
+        capi.PQIndex.create(ctx, c["coarse"], c["cb"], perm=np.zeros(128, np.int32))  # not a permutation
+    with pytest.raises(capi.B200nnError):
+        capi.PQIndex.load_model(ctx, "/nonexistent.model")
+    idx.close()
+
+
+def test_save_load_index_roundtrip(ctx, tmp_path):
+    from cvt_b200 import capi
+    c = cases.opq_case("ivf_m8")
+    idx = capi.PQIndex.create(ctx, c["coarse"], c["cb"], perm=c["reorder"])
+    groups = (np.arange(c["n"]) // 50).astype(np.int32)
+    idx.add(c["db"], groups)
+    ref_scores = idx.scores(c["q"], nprobe=3)
+    idx.save_index(str(tmp_path), [f"/data/video_{i}.bin" for i in range(idx.n_groups)])
+    path = tmp_path / f"OPQ_Index_db_{idx.n_groups}_dim_64_k_16_PQ_m8_k256.fvecs"
+    assert path.exists()
+    # byte layout of IVFOPQ::SaveIndex (IVFOPQ.cpp:544-580)
+    raw = path.read_bytes()
+    hdr = np.frombuffer(raw, dtype="<i4", count=5)
+    assert hdr.tolist() == [64, 16, 8, 256, idx.n_groups]
+    expect = 20 + 4 * (16 * 64 + 8 * 256 * 8) + 16 * 4 + c["n"] * (4 + 8) + idx.n_groups * 260
+    assert len(raw) == expect
+    idx2 = capi.PQIndex.load_index(ctx, str(path), perm=c["reorder"])
+    assert idx2.n_rows == c["n"] and idx2.n_groups == idx.n_groups
+    assert np.array_equal(_bits(idx2.scores(c["q"], nprobe=3)), _bits(ref_scores))
+    idx.close(); idx2.close()
