@@ -251,3 +251,112 @@ class PQIndex:
         if group_paths is not None:
             arr = (C.c_char_p * len(group_paths))(*[p.encode() for p in group_paths])
         _check(load().b200nn_pq_save_index(self.h, dir_or_path.encode(), arr), "pq_save_index")
+
+
+class FlatIndex:
+    """hnswlib::BruteforceSearch<float|int> drop-in surface (brute_force_search/src/brutoforce.hpp)."""
+    METRIC = {"ip": 0, "l2": 1, "l2_u8": 2}
+
+    def __init__(self, ctx: Context, metric: str, dim: int, max_elements: int, order: int = 4, _handle=None):
+        self.ctx, self.metric, self.dim = ctx, self.METRIC[metric], dim
+        self.h = C.c_void_p()
+        if _handle is not None:
+            self.h = _handle
+        else:
+            _check(load().b200nn_flat_create(ctx.h, C.c_int(self.metric), C.c_int(order), C.c_size_t(dim),
+                                             C.c_size_t(max_elements), C.byref(self.h)), "flat_create")
+        ctx._adopt(self)
+
+    @classmethod
+    def load_file(cls, ctx, metric: str, dim: int, path: str, order: int = 4):
+        h = C.c_void_p()
+        _check(load().b200nn_flat_load(ctx.h, C.c_int(cls.METRIC[metric]), C.c_int(order), C.c_size_t(dim), path.encode(),
+                                       C.byref(h)), "flat_load")
+        return cls(ctx, metric, dim, 0, order, _handle=h)
+
+    def close(self):
+        if self.h:
+            load().b200nn_flat_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _elems(self, a):
+        return np.ascontiguousarray(a, dtype=np.uint8 if self.metric == 2 else np.float32)
+
+    def add(self, vectors, labels):
+        v = self._elems(vectors)
+        l = np.ascontiguousarray(labels, dtype=np.uint64)
+        _check(load().b200nn_flat_add(self.h, _vp(v), _vp(l), C.c_size_t(v.shape[0])), "flat_add")
+
+    def remove(self, label: int):
+        _check(load().b200nn_flat_remove(self.h, C.c_uint64(label)), "flat_remove")
+
+    def __len__(self):
+        v = C.c_size_t()
+        _check(load().b200nn_flat_size(self.h, C.byref(v)), "flat_size")
+        return int(v.value)
+
+    def search(self, queries, k: int):
+        q = self._elems(queries)
+        nq = q.shape[0]
+        D = np.empty((nq, k), dtype=np.int32 if self.metric == 2 else np.float32)
+        L = np.empty((nq, k), dtype=np.uint64)
+        _check(load().b200nn_flat_search(self.h, _vp(q), C.c_size_t(nq), C.c_size_t(k), _vp(D), _vp(L)), "flat_search")
+        return D, L
+
+    def search_dev(self, q_dev_ptr: int, nq: int, k: int, out_dist_ptr: int, out_label_ptr: int):
+        _check(load().b200nn_flat_search_dev(self.h, C.c_void_p(q_dev_ptr), C.c_size_t(nq), C.c_size_t(k),
+                                             C.c_void_p(out_dist_ptr), C.c_void_p(out_label_ptr)), "flat_search_dev")
+
+    def save(self, path: str):
+        _check(load().b200nn_flat_save(self.h, path.encode()), "flat_save")
+
+
+class SQ:
+    """cvtk::quant::Int8Quan drop-in surface (scalar_quantization/scalar_quantization/int8_quan.h)."""
+
+    def __init__(self, ctx: Context, vmin, vdiff):
+        self.ctx = ctx
+        vmin, vdiff = _f32(vmin), _f32(vdiff)
+        self.d = vmin.shape[0]
+        self.h = C.c_void_p()
+        _check(load().b200nn_sq_create(ctx.h, C.c_int(self.d), _vp(vmin), _vp(vdiff), C.byref(self.h)), "sq_create")
+        ctx._adopt(self)
+
+    def close(self):
+        if self.h:
+            load().b200nn_sq_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def train_minmax(ctx: Context, x_normed):
+        x = _f32(x_normed)
+        vmin = np.empty(x.shape[1], dtype=np.float32)
+        vdiff = np.empty(x.shape[1], dtype=np.float32)
+        _check(load().b200nn_sq_train_minmax(ctx.h, C.c_int(x.shape[1]), _vp(x), C.c_size_t(x.shape[0]), _vp(vmin), _vp(vdiff)),
+               "sq_train_minmax")
+        return vmin, vdiff
+
+    def encode(self, x, l2norm=True):
+        """Returns (codes, x_after): like the reference, x is normalised in place when l2norm."""
+        x = _f32(x).copy()
+        codes = np.empty(x.shape, dtype=np.uint8)
+        _check(load().b200nn_sq_encode(self.h, _vp(x), C.c_size_t(x.shape[0]), C.c_int(int(l2norm)), _vp(codes)), "sq_encode")
+        return codes, x
+
+    def decode(self, codes, faiss_float=False):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        x = np.empty(codes.shape, dtype=np.float32)
+        _check(load().b200nn_sq_decode(self.h, _vp(codes), C.c_size_t(codes.shape[0]), C.c_int(int(faiss_float)), _vp(x)), "sq_decode")
+        return x

@@ -1,0 +1,250 @@
+// capi_flat.cu -- C ABI of the exact flat index: hnswlib::BruteforceSearch<float|int> drop-in
+// (brute_force_search/src/brutoforce.hpp:8-136; identical copy hnsw_sifts_retrieval/hnswlib/brutoforce.h).
+#include <stdio.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+
+#include "capi_common.cuh"
+#include "flat_kernels.cuh"
+#include "topk.cuh"
+
+using namespace b200nn;
+
+struct b200nn_flat {
+    b200nn_ctx* ctx = nullptr;
+    int metric = 0, order = 4;
+    size_t dim = 0, max_elements = 0, row_bytes = 0;
+    size_t n = 0;
+    DevBuf<unsigned char> data;                 // [max_elements][row_bytes]
+    std::vector<uint64_t> labels;               // host mirror, row order
+    std::unordered_map<uint64_t, size_t> l2r;   // dict_external_to_internal, brutoforce.hpp:41
+    bool ranks_valid = false;
+    DevBuf<uint32_t> rank;                      // rank of each row's label
+    DevBuf<unsigned long long> label_sorted;    // rank -> label
+    DevBuf<unsigned char> ws_q;
+    DevBuf<unsigned long long> ws_keys, ws_id;
+    DevBuf<float> ws_dist;
+};
+
+namespace {
+
+struct FGuard {
+    std::lock_guard<std::mutex> g;
+    explicit FGuard(b200nn_flat* p) : g(p->ctx->mu) { cudaSetDevice(p->ctx->c.device); }
+};
+
+int flat_new(b200nn_ctx_t ctx, int metric, int order, size_t dim, size_t max_elements, b200nn_flat_t* out) {
+    if (!ctx || !out) B2_FAIL(B200NN_ERR_INVALID, "flat_create: NULL argument");
+    if (metric < 0 || metric > 2 || dim == 0) B2_FAIL(B200NN_ERR_INVALID, "flat_create: bad metric or dim");
+    if (metric != 2) {
+        if (order != 1 && order != 4 && order != 8) B2_FAIL(B200NN_ERR_INVALID, "flat_create: order must be 1, 4 or 8");
+        // the reference picks the kernel from the dimension (space_ip.hpp:217-225, space_l2.h:159-164)
+        if (order == 8 && dim % 16 != 0) B2_FAIL(B200NN_ERR_UNSUPPORTED, "flat_create: AVX order (8) needs dim % 16 == 0");
+        if (order == 4 && dim % 4 != 0) B2_FAIL(B200NN_ERR_UNSUPPORTED, "flat_create: SSE order (4) needs dim % 4 == 0");
+    }
+    if (max_elements >= 0xFFFFFFFFull) B2_FAIL(B200NN_ERR_UNSUPPORTED, "flat_create: at most 2^32-2 rows per index");
+    b200nn_flat* p = new b200nn_flat();
+    p->ctx = ctx; p->metric = metric; p->order = metric == 2 ? 0 : order; p->dim = dim; p->max_elements = max_elements;
+    p->row_bytes = metric == 2 ? dim : dim * sizeof(float);
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->c.device);
+    int rc = p->data.ensure(std::max<size_t>(1, max_elements) * p->row_bytes);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return 0;
+}
+
+int ensure_ranks(b200nn_flat* p) {
+    if (p->ranks_valid) return 0;
+    Ctx* c = &p->ctx->c;
+    const size_t n = p->n;
+    std::vector<uint32_t> order(n), rank(n);
+    std::iota(order.begin(), order.end(), 0u);
+    bool sorted = true;
+    for (size_t i = 1; i < n && sorted; i++) sorted = p->labels[i - 1] < p->labels[i];
+    if (!sorted) std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return p->labels[a] < p->labels[b]; });
+    std::vector<unsigned long long> ls(n);
+    for (size_t r = 0; r < n; r++) { rank[order[r]] = (uint32_t)r; ls[r] = p->labels[order[r]]; }
+    int rc;
+    if ((rc = p->rank.ensure(std::max<size_t>(1, n))) || (rc = p->label_sorted.ensure(std::max<size_t>(1, n)))) return rc;
+    if (n) {
+        B2_CUDA(cudaMemcpyAsync(p->rank.p, rank.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+        B2_CUDA(cudaMemcpyAsync(p->label_sorted.p, ls.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    p->ranks_valid = true;
+    return 0;
+}
+
+int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, void* out_dist, unsigned long long* out_label) {
+    Ctx* c = &p->ctx->c;
+    if (!nq) return 0;
+    if (k < 1 || k > (size_t)KP) B2_FAIL(B200NN_ERR_UNSUPPORTED, "flat_search: k must be in [1, 128]");
+    int rc;
+    if ((rc = ensure_ranks(p))) return rc;
+    const int S = flat_pick_slices(c->sm_count, (long long)nq, (long long)p->n);
+    if ((rc = p->ws_keys.ensure((size_t)S * nq * k))) return rc;
+    if ((rc = launch_flat_scan(c, p->metric, p->order, p->data.p, p->rank.p, (long long)p->n, (int)p->dim, q_dev, (long long)nq, S,
+                               (int)k, p->ws_keys.p)))
+        return rc;
+    if ((rc = launch_topk_merge(c, p->ws_keys.p, S, (long long)nq, (int)k, (long long)(nq * k), p->metric == 2 ? nullptr : (float*)out_dist,
+                                p->metric == 2 ? (int*)out_dist : nullptr, out_label, nullptr)))
+        return rc;
+    return launch_rank_to_label(c, out_label, (long long)(nq * k), p->label_sorted.p);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200nn_flat_create(b200nn_ctx_t ctx, int metric, int order, size_t dim, size_t max_elements, b200nn_flat_t* out) {
+    return flat_new(ctx, metric, order, dim, max_elements, out);
+}
+
+void b200nn_flat_destroy(b200nn_flat_t p) {
+    if (!p) return;
+    {
+        FGuard g(p);
+        cudaStreamSynchronize(p->ctx->c.stream);
+    }
+    delete p;
+}
+
+int b200nn_flat_add(b200nn_flat_t p, const void* vectors, const uint64_t* labels, size_t n) {
+    if (!p || (n && (!vectors || !labels))) B2_FAIL(B200NN_ERR_INVALID, "flat_add: NULL argument");
+    if (!n) return 0;
+    FGuard g(p);
+    // validate the whole batch first, in addPoint's own order of checks per element
+    // (duplicate label, then capacity; brutoforce.hpp:44-50); nothing is added if any row fails
+    {
+        std::unordered_map<uint64_t, size_t> seen;
+        for (size_t i = 0; i < n; i++) {
+            if (p->l2r.count(labels[i]) || !seen.emplace(labels[i], i).second) B2_FAIL(B200NN_ERR_STATE, "Ids have to be unique");
+            if (p->n + i >= p->max_elements) B2_FAIL(B200NN_ERR_STATE, "The number of elements exceeds the specified limit\n");
+        }
+    }
+    Ctx* c = &p->ctx->c;
+    B2_CUDA(cudaMemcpyAsync(p->data.p + p->n * p->row_bytes, vectors, n * p->row_bytes, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; i++) {
+        p->l2r[labels[i]] = p->n + i;
+        p->labels.push_back(labels[i]);
+    }
+    p->n += n;
+    p->ranks_valid = false;
+    return 0;
+}
+
+// removePoint, brutoforce.hpp:58-70: the last element moves into the hole.
+int b200nn_flat_remove(b200nn_flat_t p, uint64_t label) {
+    if (!p) B2_FAIL(B200NN_ERR_INVALID, "flat is NULL");
+    FGuard g(p);
+    auto it = p->l2r.find(label);
+    if (it == p->l2r.end()) B2_FAIL(B200NN_ERR_STATE, "flat_remove: label not found");
+    const size_t cur = it->second, last = p->n - 1;
+    Ctx* c = &p->ctx->c;
+    p->l2r.erase(it);
+    if (cur != last) {
+        B2_CUDA(cudaMemcpyAsync(p->data.p + cur * p->row_bytes, p->data.p + last * p->row_bytes, p->row_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+        p->labels[cur] = p->labels[last];
+        p->l2r[p->labels[cur]] = cur;
+    }
+    p->labels.pop_back();
+    p->n--;
+    p->ranks_valid = false;
+    return 0;
+}
+
+int b200nn_flat_size(b200nn_flat_t p, size_t* out) {
+    if (!p || !out) B2_FAIL(B200NN_ERR_INVALID, "NULL argument");
+    *out = p->n;
+    return 0;
+}
+
+int b200nn_flat_search_dev(b200nn_flat_t p, const void* q_dev, size_t nq, size_t k, void* out_dist_dev, uint64_t* out_label_dev) {
+    if (!p || (nq && (!q_dev || !out_dist_dev || !out_label_dev))) B2_FAIL(B200NN_ERR_INVALID, "flat_search_dev: NULL argument");
+    FGuard g(p);
+    return search_dev_locked(p, q_dev, nq, k, out_dist_dev, (unsigned long long*)out_label_dev);
+}
+
+int b200nn_flat_search(b200nn_flat_t p, const void* queries, size_t nq, size_t k, void* out_dist, uint64_t* out_label) {
+    if (!p || (nq && (!queries || !out_dist || !out_label))) B2_FAIL(B200NN_ERR_INVALID, "flat_search: NULL argument");
+    if (!nq) return 0;
+    FGuard g(p);
+    Ctx* c = &p->ctx->c;
+    int rc;
+    if ((rc = p->ws_q.ensure(nq * p->row_bytes)) || (rc = p->ws_dist.ensure(nq * k)) || (rc = p->ws_id.ensure(nq * k))) return rc;
+    B2_CUDA(cudaMemcpyAsync(p->ws_q.p, queries, nq * p->row_bytes, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = search_dev_locked(p, p->ws_q.p, nq, k, p->ws_dist.p, p->ws_id.p))) return rc;
+    B2_CUDA(cudaMemcpyAsync(out_dist, p->ws_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaMemcpyAsync(out_label, p->ws_id.p, nq * k * 8, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// saveIndex byte format, brutoforce.hpp:95-106: size_t maxelements_, size_per_element_, cur_element_count,
+// then maxelements_ x [vector bytes | size_t label].  Unused slots are zero (the reference leaves
+// them uninitialised).
+int b200nn_flat_save(b200nn_flat_t p, const char* path) {
+    if (!p || !path) B2_FAIL(B200NN_ERR_INVALID, "flat_save: NULL argument");
+    FGuard g(p);
+    Ctx* c = &p->ctx->c;
+    std::vector<unsigned char> rows(p->n * p->row_bytes);
+    if (p->n) {
+        B2_CUDA(cudaMemcpyAsync(rows.data(), p->data.p, rows.size(), cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) B2_FAIL(B200NN_ERR_IO, std::string("flat_save: cannot open ") + path);
+    const size_t spe = p->row_bytes + sizeof(size_t);
+    const size_t hdr[3] = {p->max_elements, spe, p->n};
+    fwrite(hdr, sizeof(size_t), 3, f);
+    std::vector<unsigned char> el(spe, 0);
+    for (size_t i = 0; i < p->max_elements; i++) {
+        if (i < p->n) {
+            memcpy(el.data(), rows.data() + i * p->row_bytes, p->row_bytes);
+            const size_t lab = (size_t)p->labels[i];
+            memcpy(el.data() + p->row_bytes, &lab, sizeof(size_t));
+        } else {
+            memset(el.data(), 0, spe);
+        }
+        fwrite(el.data(), 1, spe, f);
+    }
+    const bool ok = !ferror(f);
+    fclose(f);
+    if (!ok) B2_FAIL(B200NN_ERR_IO, "flat_save: write failed");
+    return 0;
+}
+
+// loadIndex, brutoforce.hpp:108-134: sizes are re-derived from the space (metric, dim), as the reference does.
+int b200nn_flat_load(b200nn_ctx_t ctx, int metric, int order, size_t dim, const char* path, b200nn_flat_t* out) {
+    if (!ctx || !path || !out) B2_FAIL(B200NN_ERR_INVALID, "flat_load: NULL argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) B2_FAIL(B200NN_ERR_IO, std::string("flat_load: cannot open ") + path);
+    size_t hdr[3];
+    if (fread(hdr, sizeof(size_t), 3, f) != 3) { fclose(f); B2_FAIL(B200NN_ERR_IO, "flat_load: truncated header"); }
+    const size_t row_bytes = metric == 2 ? dim : dim * 4, spe = row_bytes + sizeof(size_t);
+    if (hdr[1] != spe || hdr[2] > hdr[0]) { fclose(f); B2_FAIL(B200NN_ERR_IO, "flat_load: element size does not match metric/dim"); }
+    int rc = flat_new(ctx, metric, order, dim, hdr[0], out);
+    if (rc) { fclose(f); return rc; }
+    const size_t n = hdr[2];
+    std::vector<unsigned char> rows(n * row_bytes), el(spe);
+    std::vector<uint64_t> labels(n);
+    for (size_t i = 0; i < n; i++) {
+        if (fread(el.data(), 1, spe, f) != spe) { fclose(f); b200nn_flat_destroy(*out); *out = nullptr; B2_FAIL(B200NN_ERR_IO, "flat_load: truncated data"); }
+        memcpy(rows.data() + i * row_bytes, el.data(), row_bytes);
+        size_t lab;
+        memcpy(&lab, el.data() + row_bytes, sizeof(size_t));
+        labels[i] = lab;
+    }
+    fclose(f);
+    rc = b200nn_flat_add(*out, rows.data(), labels.data(), n);
+    if (rc) { b200nn_flat_destroy(*out); *out = nullptr; }
+    return rc;
+}
+
+}  // extern "C"

@@ -344,7 +344,7 @@ ORC_API void orc_sq_l2normalize(float* v, int d) {
     double accum = 0.0;
     for (int i = 0; i < d; ++i) accum += v[i] * v[i];
     accum = sqrt(accum);
-    float denorm_v = (float)(1e-12 > accum ? 1e-12 : accum);
+    float denorm_v = (float)(1e-12 < accum ? accum : 1e-12); /* std::max((double)1e-12, (double)accum) */
     for (int i = 0; i < d; ++i) v[i] = v[i] / denorm_v;
 }
 
