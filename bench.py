@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark of the quantized nearest-neighbour path.
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's own CPU scan
+
+Workload (default `cfg3`, BASELINE.json configs[2], the configuration the metric is quoted on):
+OPQ M=16 8-bit sub-codes, 1M x 128-d SIFT-shaped unit-norm vectors, flat (K=1) ADC scan, top-100
+(recall@10 reported), batch 4096, clamp threshold 1.0 as in the reference.  A "step" = one pass of
+the hot path over one query batch: rotate -> LUT build -> ADC scan + top-k -> slice merge
+[-> all-gather of shard top-k + merge when N > 1].  With N > 1 the SAME database is row-sharded
+over the ranks ("scaling": "strong"); the query batch is replicated.
+
+Prints ONE JSON line on rank 0 (see README/DESIGN for the fields).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cvt_b200 import synth  # noqa: E402
+
+WORKLOADS = {
+    # name: n_rows, D, M, batch, k
+    "cfg3": dict(n=1_000_000, D=128, M=16, B=4096, k=100, desc="cfg3: OPQ M=16 8-bit, 1M x 128 SIFT-shaped, flat ADC top-100, batch 4096"),
+    "cfg3_small": dict(n=100_000, D=128, M=16, B=512, k=100, desc="cfg3 shape at 1/10 size (development)"),
+    "cfg4_shard": dict(n=1_250_000, D=512, M=32, B=4096, k=100, desc="cfg4 per-GPU shard: OPQ M=32, 1.25M x 512 CNN-like, ADC top-100, batch 4096"),
+}
+METRIC = "queries/sec, batched ADC top-k scan (HBM GB/s in roofline; recall@10 vs CPU reference)"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def make_inputs(wl):
+    """Seeded host inputs, identical on every rank and for both arms."""
+    n, D, M, B = wl["n"], wl["D"], wl["M"], wl["B"]
+    if D == 128:
+        db = synth.sift_like(n, D, seed=synth.SEED_DB)
+        q = synth.sift_like(B, D, seed=synth.SEED_QUERY)
+        perm = synth.SHIPPED_REORDER_128
+    else:
+        db = synth.cnn_like(n, D, seed=synth.SEED_DB)
+        q = synth.cnn_like(B, D, seed=synth.SEED_QUERY)
+        perm = synth.random_permutation(D)
+    coarse, cb = synth.train_pq_model(db[:20000][:, perm], M, 256, 1, iters=6, seed=synth.SEED_KMEANS, train_rows=20000)
+    return db, q, perm.astype(np.int32), coarse, cb
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def write_reference_inputs(td, db, q, perm, coarse, cb):
+    """The reference's own byte formats: .model (IVFOPQ::LoadModel) + raw feature files."""
+    model = os.path.join(td, "bench.model")
+    synth.write_opq_model(model, coarse, cb, perm)
+    dbf, qf = os.path.join(td, "db.bin"), os.path.join(td, "q.bin")
+    synth.write_feat_file(dbf, db)
+    synth.write_feat_file(qf, q)
+    return model, dbf, qf
+
+
+def run_reference_sample(wl, inputs, n_queries, repeat, threads=0):
+    """Time the UNMODIFIED reference (oracle/_ref/ref_opq: IVFOPQ::Add to build, QueryThrehold +
+    get_sort_results to search) on a bounded query sample over all host threads."""
+    from oracle import oracle as orc  # test infrastructure: the checker / CPU baseline, never the product path
+    if not orc.have_ref("ref_opq"):
+        raise RuntimeError("oracle/_ref/ref_opq is missing (it is built in the container where /root/reference exists)")
+    db, q, perm, coarse, cb = inputs
+    td = tempfile.mkdtemp(prefix="b200nn_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        model, dbf, qf = write_reference_inputs(td, db, q, perm, coarse, cb)
+        r = orc.bench_ref_opq(model, dbf, qf, nk=1, topk=wl["k"], n_queries=n_queries, threads=threads, tmpdir=td, repeat=repeat)
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+    return r
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=64, help="queries of the batch timed on the host cores")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    n, D, M, B, k = wl["n"], wl["D"], wl["M"], wl["B"], wl["k"]
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        inputs = make_inputs(wl)
+        ns = min(B, args.cpu_sample)
+        r = run_reference_sample(wl, inputs, ns, repeat=args.steps + args.warmup)
+        qps = ns / r["query_s_mean"]
+        line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * r["query_s_mean"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["desc"], "n_rows": n, "dim": D, "M": M, "batch": B, "k": k, "nprobe": 1,
+                           "step": f"{ns}-query sample of the batch per step"},
+                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": r["threads"], "kind": "reference",
+                                 "sample": f"{ns} of {B} queries per step x {args.steps + args.warmup} steps, unmodified IVFOPQ::QueryThrehold + "
+                                           f"get_sort_results over {r['threads']} OpenMP threads; index built by IVFOPQ::Add in {r['build_s']:.1f}s"},
+                "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import torch
+    import torch.distributed as dist
+    from cvt_b200 import capi, sharded
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    # a dedicated non-default stream shared by torch (flush, events, NCCL ordering) and the library
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    inputs = make_inputs(wl)
+    db, q, perm, coarse, cb = inputs
+    lo, hi = sharded.shard_bounds(n, world, rank)
+    ctx = capi.Context(local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    index = capi.PQIndex.create(ctx, coarse, cb, perm=perm, clamp=1.0)
+    index.add(db[lo:hi])
+    sh = sharded.make_gpu_sharded(ctx, index, dist, rank, world, id_base=lo, nprobe=1)
+
+    q_pinned = torch.from_numpy(q).pin_memory()
+    q_dev = q_pinned.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    out_d_host = torch.empty((B, k), dtype=torch.float32).pin_memory()
+    out_i_host = torch.empty((B, k), dtype=torch.int64).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ("value"): inputs in HBM, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        dd, ii = sh.search(q_dev, k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_ms = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()  # evict L2 between timed iterations (outside the event pair)
+        ev[s][0].record()
+        dd, ii = sh.search(q_dev, k)
+        ev[s][1].record()
+        ev[s][1].synchronize()
+        stage_ms.append(index.last_timing())
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    qps = B / (ms_per_step * 1e-3)
+    scan_ms = float(np.mean([t["scan_ms"] for t in stage_ms]))
+    result_ids = ii.cpu().numpy()
+    result_d = dd.cpu().numpy()
+
+    # ---- end-to-end through the public C-ABI call with HOST buffers (H2D + D2H inside the timed region)
+    def e2e_step():
+        if world == 1:
+            index.search_host_ptr(q_pinned.data_ptr(), B, k, 1, out_d_host.data_ptr(), out_i_host.data_ptr())
+        else:
+            qd = q_pinned.to(dev, non_blocking=True)
+            d2, i2 = sh.search(qd, k)
+            out_d_host.copy_(d2, non_blocking=True)
+            out_i_host.copy_(i2, non_blocking=True)
+            torch.cuda.synchronize()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_qps = B / float(e2e_s.item())
+    assert np.array_equal(out_i_host.numpy(), result_ids), "e2e path and device path disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak_hbm()
+    alg_bytes = float(B) * (hi - lo) * M  # every query "reads" every code byte of the shard once
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {"metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (LUT sums) over u8 codes", "data": "synthetic",
+            "config": {"workload": wl["desc"], "n_rows": n, "rows_per_gpu": hi - lo, "dim": D, "M": M, "ksub": 256, "batch": B, "k": k,
+                       "nprobe": 1, "clamp": 1.0, "parallelism": f"row-sharded x{world}, one all-gather of top-k keys" if world > 1 else "single GPU",
+                       "l2": "256 MB buffer written between timed iterations (L2 flush)", "seeds": "SURVEY.md §8(d)"},
+            "roofline": {"bound": "hbm", "kernel": "adc_scan_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms,
+                         "note": "algorithmic bytes = batch x shard rows x M; binding unit is the shared-memory gather pipe (DESIGN.md)"},
+            "stage_ms": {kk: float(np.mean([t[kk] for t in stage_ms])) for kk in stage_ms[0]},
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(B * D * 4), "d2h_bytes_per_step": int(B * k * 12)},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the unmodified reference on a bounded sample, + parity
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ns = min(B, args.cpu_sample)
+            r = run_reference_sample(wl, inputs, ns, repeat=1)
+            cpu_qps = ns / r["query_s_mean"]
+            ids_equal = bool(np.array_equal(r["topk_id"], result_ids[:ns]))
+            rel = np.abs(r["topk_score"] - result_d[:ns]) / np.maximum(np.abs(r["topk_score"]), 1e-30)
+            recall10 = float(np.mean([len(set(r["topk_id"][i, :10]) & set(result_ids[i, :10])) / 10.0 for i in range(ns)]))
+            line["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": r["threads"], "kind": "reference",
+                                    "sample": f"first {ns} of {B} queries, unmodified IVFOPQ::QueryThrehold + get_sort_results over "
+                                              f"{r['threads']} OpenMP threads (index built by IVFOPQ::Add, {r['build_s']:.1f}s, untimed)"}
+            line["parity"] = {"vs": "unmodified reference (oracle/_ref/ref_opq)", "queries_checked": ns, "topk_ids_identical": ids_equal,
+                              "recall_at_10": recall10, "max_rel_dist_err": float(rel.max()),
+                              "scores_bit_identical": bool(np.array_equal(r["topk_score"].view(np.uint32), result_d[:ns].view(np.uint32)))}
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
+    else:
+        line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference",
+                                "sample": "timed at N=1 only (see the N=1 line)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

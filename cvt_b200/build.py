@@ -79,7 +79,18 @@ def build_tools(force: bool = False, verbose: bool = False):
         outs.append(o)
         if force or _newer([s, LIB] + hdrs, o):
             _run([gxx, "-O2", "-std=c++14", "-I", os.path.join(ROOT, "include"), s, "-o", o, "-L", LIBDIR, "-lb200nn",
-                  "-Wl,-rpath," + LIBDIR], o + ".log")
+                  "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../../cvt_b200/lib"], o + ".log")
+    # the reference's OWN brute-force CLI, unmodified, compiled in place against the forwarding
+    # headers and linked with libb200nn: the drop-in proof (only where /root/reference exists; the
+    # binary then travels with the snapshot)
+    ref_src = "/root/reference/brute_force_search/src/brute_force.cpp"
+    o = os.path.join(bdir, "ref_brute_force_on_b200nn")
+    if os.path.exists(ref_src):
+        if force or _newer([ref_src, LIB] + hdrs, o):
+            _run([gxx, "-O2", "-std=c++11", "-fno-operator-names", "-I", os.path.join(ROOT, "include", "b200nn", "compat"),
+                  ref_src, "-o", o, "-L", LIBDIR, "-lb200nn", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../../cvt_b200/lib"], o + ".log")
+    if os.path.exists(o):
+        outs.append(o)
     return outs
 
 

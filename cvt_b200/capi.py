@@ -22,7 +22,7 @@ SYMBOLS = [
     "b200nn_flat_create", "b200nn_flat_destroy", "b200nn_flat_add", "b200nn_flat_remove", "b200nn_flat_size",
     "b200nn_flat_search", "b200nn_flat_search_dev", "b200nn_flat_save", "b200nn_flat_load",
     "b200nn_pq_create", "b200nn_pq_load_model", "b200nn_pq_destroy", "b200nn_pq_set_clamp", "b200nn_pq_info",
-    "b200nn_pq_rotate", "b200nn_pq_encode", "b200nn_pq_add", "b200nn_pq_add_dev", "b200nn_pq_get_rows",
+    "b200nn_pq_rotate", "b200nn_pq_encode", "b200nn_pq_add", "b200nn_pq_add_dev", "b200nn_pq_add_rotated", "b200nn_pq_get_rows",
     "b200nn_pq_build_lut", "b200nn_pq_scores", "b200nn_pq_search", "b200nn_pq_search_dev", "b200nn_topk_merge_dev",
     "b200nn_pq_save_index", "b200nn_pq_load_index", "b200nn_pq_last_timing", "b200nn_pq_scan_bytes",
     "b200nn_sq_create", "b200nn_sq_destroy", "b200nn_sq_train_minmax", "b200nn_sq_encode", "b200nn_sq_decode",
@@ -196,6 +196,11 @@ class PQIndex:
         x_raw = _f32(x_raw)
         g = None if group_ids is None else np.ascontiguousarray(group_ids, dtype=np.int32)
         _check(load().b200nn_pq_add(self.h, _vp(x_raw), C.c_size_t(x_raw.shape[0]), _vp(g)), "pq_add")
+
+    def add_rotated(self, x_rot, group_ids=None):
+        x_rot = _f32(x_rot)
+        g = None if group_ids is None else np.ascontiguousarray(group_ids, dtype=np.int32)
+        _check(load().b200nn_pq_add_rotated(self.h, _vp(x_rot), C.c_size_t(x_rot.shape[0]), _vp(g)), "pq_add_rotated")
 
     def add_dev(self, x_dev_ptr: int, n: int, group_dev_ptr: int | None = None):
         _check(load().b200nn_pq_add_dev(self.h, C.c_void_p(x_dev_ptr), C.c_size_t(n), C.c_void_p(group_dev_ptr or 0)), "pq_add_dev")

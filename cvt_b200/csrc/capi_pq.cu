@@ -138,7 +138,8 @@ int encode_dev(b200nn_pq* p, const float* x_rot, long long n, int* list, unsigne
     return launch_pq_encode(c, x_rot, n, p->D, p->coarse.p, list, p->cbT.p, p->M, p->ksub, codes);
 }
 
-int add_dev_locked(b200nn_pq* p, const float* x_dev, long long nn, const int* group_dev, const int* group_host) {
+int add_dev_locked(b200nn_pq* p, const float* x_dev, long long nn, const int* group_dev, const int* group_host,
+                   bool already_rotated = false) {
     Ctx* c = &p->ctx->c;
     if (nn <= 0) return 0;
     if (p->n + nn > 0x7fffffffLL) B2_FAIL(B200NN_ERR_STATE, "pq_add: more than 2^31-1 rows per shard");
@@ -147,11 +148,11 @@ int add_dev_locked(b200nn_pq* p, const float* x_dev, long long nn, const int* gr
     if ((rc = p->list.reserve((size_t)(p->n + nn), (size_t)p->n, c->stream))) return rc;
     if ((rc = p->group.reserve((size_t)(p->n + nn), (size_t)p->n, c->stream))) return rc;
     const long long chunk = 1 << 18;
-    if (p->has_perm && (rc = p->ws_x.ensure((size_t)std::min(chunk, nn) * p->D))) return rc;
+    if (p->has_perm && !already_rotated && (rc = p->ws_x.ensure((size_t)std::min(chunk, nn) * p->D))) return rc;
     for (long long off = 0; off < nn; off += chunk) {
         const long long cn = std::min(chunk, nn - off);
-        const float* xr = nullptr;
-        if ((rc = rotate_dev(p, x_dev + off * p->D, cn, p->ws_x.p, &xr))) return rc;
+        const float* xr = x_dev + off * p->D;
+        if (!already_rotated && (rc = rotate_dev(p, x_dev + off * p->D, cn, p->ws_x.p, &xr))) return rc;
         if ((rc = encode_dev(p, xr, cn, p->list.p + p->n + off, p->codes.p + (p->n + off) * p->M))) return rc;
     }
     if (group_dev) {
@@ -382,7 +383,17 @@ int b200nn_pq_encode(b200nn_pq_t p, const float* x_rot, size_t n, int32_t* out_l
     return 0;
 }
 
+static int pq_add_host(b200nn_pq_t p, const float* x_raw, size_t n, const int32_t* group_ids, bool already_rotated);
+
 int b200nn_pq_add(b200nn_pq_t p, const float* x_raw, size_t n, const int32_t* group_ids) {
+    return pq_add_host(p, x_raw, n, group_ids, false);
+}
+
+int b200nn_pq_add_rotated(b200nn_pq_t p, const float* x_rotated, size_t n, const int32_t* group_ids) {
+    return pq_add_host(p, x_rotated, n, group_ids, true);
+}
+
+static int pq_add_host(b200nn_pq_t p, const float* x_raw, size_t n, const int32_t* group_ids, bool already_rotated) {
     if (!p || (n && !x_raw)) B2_FAIL(B200NN_ERR_INVALID, "pq_add: NULL argument");
     if (!n) return 0;
     Guard g(p);
@@ -398,7 +409,8 @@ int b200nn_pq_add(b200nn_pq_t p, const float* x_raw, size_t n, const int32_t* gr
         const size_t cn = std::min(chunk, n - off);
         B2_CUDA(cudaMemcpyAsync(stage.p, x_raw + off * p->D, sizeof(float) * cn * p->D, cudaMemcpyHostToDevice, c->stream));
         if (group_ids) B2_CUDA(cudaMemcpyAsync(gstage.p, group_ids + off, sizeof(int) * cn, cudaMemcpyHostToDevice, c->stream));
-        if ((rc = add_dev_locked(p, stage.p, (long long)cn, group_ids ? gstage.p : nullptr, group_ids ? group_ids + off : nullptr)))
+        if ((rc = add_dev_locked(p, stage.p, (long long)cn, group_ids ? gstage.p : nullptr, group_ids ? group_ids + off : nullptr,
+                                 already_rotated)))
             return rc;
     }
     B2_CUDA(cudaStreamSynchronize(c->stream));

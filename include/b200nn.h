@@ -96,6 +96,8 @@ int b200nn_pq_encode(b200nn_pq_t idx, const float* x_rotated, size_t n, int32_t*
 /* rotate + encode + append.  group_ids = videoId per row (NULL: one new group per row, id = row). */
 int b200nn_pq_add(b200nn_pq_t idx, const float* x_raw, size_t n, const int32_t* group_ids);
 int b200nn_pq_add_dev(b200nn_pq_t idx, const float* x_raw_dev, size_t n, const int32_t* group_ids_dev);
+/* IVFOPQ::Add proper: rows that LoadSingleFeatFile already reordered (IVFOPQ.cpp:459-461) -> encode + append. */
+int b200nn_pq_add_rotated(b200nn_pq_t idx, const float* x_rotated, size_t n, const int32_t* group_ids);
 /* read back what Add stored, rows [start, start+n) in insertion order. */
 int b200nn_pq_get_rows(b200nn_pq_t idx, uint64_t start, size_t n, int32_t* out_list, int32_t* out_group,
                        uint8_t* out_codes);

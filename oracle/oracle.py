@@ -227,13 +227,22 @@ def run_ref_opq(model: str, db_files, query_files, nk: int, topk: int, per_row: 
 
 def bench_ref_opq(model: str, db_file: str, query_file: str, nk: int, topk: int, n_queries: int, threads: int,
                   tmpdir: str, repeat: int = 1) -> dict:
+    """Time the unmodified reference's QueryThrehold + get_sort_results on n_queries rows over
+    `threads` host threads; also returns its top-k (scores, ids) for the parity check."""
     exe = os.path.join(REF_DIR, "ref_opq")
+    dump = os.path.join(tmpdir, "ref_topk.bin")
     cmd = [exe, "bench", model, db_file, query_file, str(nk), str(topk), str(n_queries), str(threads), tmpdir,
-           str(repeat)]
+           str(repeat), dump]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"ref_opq bench failed: {r.stderr}")
-    return json.loads(r.stdout.strip().splitlines()[-1])
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    raw = np.fromfile(dump, dtype=np.uint8)
+    half = n_queries * topk * 4
+    out["topk_score"] = raw[:half].view("<f4").reshape(n_queries, topk).copy()
+    out["topk_id"] = raw[half:].view("<u4").reshape(n_queries, topk).astype(np.int64)
+    os.unlink(dump)
+    return out
 
 
 def run_ref_flat(flavour: str, metric: str, data, labels, queries, k: int, save_index: str | None = None):

@@ -172,7 +172,7 @@ static int cmd_run(int argc, char** argv) {
     return 0;
 }
 
-// bench <model> <db_feat_file> <query_feat_file> <nk> <topk> <n_queries> <threads> <tmpdir> [repeat]
+// bench <model> <db_feat_file> <query_feat_file> <nk> <topk> <n_queries> <threads> <tmpdir> [repeat] [dump.bin]
 // Builds the index with the reference's own Add (per-row ids), then times
 // QueryThrehold + get_sort_results over n_queries query rows sharded across OpenMP threads
 // (the reference itself is single-threaded; one IVFOPQ object is shared read-only).
@@ -182,6 +182,7 @@ static int cmd_bench(int argc, char** argv) {
     int nk = atoi(argv[5]), topk = atoi(argv[6]), nq = atoi(argv[7]), threads = atoi(argv[8]);
     std::string tmpdir = argv[9];
     int repeat = argc > 10 ? atoi(argv[10]) : 1;
+    const char* dump = argc > 11 ? argv[11] : NULL;
     if (threads <= 0) threads = omp_get_max_threads();
 
     mute();
@@ -227,6 +228,8 @@ static int cmd_bench(int argc, char** argv) {
     }
     std::vector<unsigned> first_ids(nq, 0);
     std::vector<float> first_scores(nq, 0.f);
+    std::vector<unsigned> all_ids((size_t)nq * topk, 0);
+    std::vector<float> all_scores((size_t)nq * topk, 0.f);
     double best = 1e30, total = 0;
     for (int rep = 0; rep < repeat; rep++) {
         double t1 = now_s();
@@ -238,6 +241,10 @@ static int cmd_bench(int argc, char** argv) {
                 std::vector<std::pair<float, uint> > r = get_sort_results(score[f], topk);
                 first_ids[i * per_file + f] = r[0].second;
                 first_scores[i * per_file + f] = r[0].first;
+                for (int j = 0; j < topk; j++) {
+                    all_ids[(size_t)(i * per_file + f) * topk + j] = r[j].second;
+                    all_scores[(size_t)(i * per_file + f) * topk + j] = r[j].first;
+                }
             }
         }
         double dt = now_s() - t1;
@@ -246,6 +253,14 @@ static int cmd_bench(int argc, char** argv) {
     }
     for (int i = 0; i < nfiles; i++) unlink(qpaths[i].c_str());
     unmute();
+    if (dump) {  // [nq][topk] scores (f32) then [nq][topk] ids (u32), for the parity check next to the timing
+        FILE* fd = fopen(dump, "wb");
+        if (fd) {
+            fwrite(all_scores.data(), sizeof(float), all_scores.size(), fd);
+            fwrite(all_ids.data(), sizeof(unsigned), all_ids.size(), fd);
+            fclose(fd);
+        }
+    }
     unsigned long long chk = 0;
     for (int i = 0; i < nq; i++) chk = chk * 1315423911ull + first_ids[i];
     printf("{\"n_rows\": %d, \"n_queries\": %d, \"threads\": %d, \"repeat\": %d, \"build_s\": %.6f, "

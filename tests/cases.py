@@ -109,3 +109,24 @@ def sq_case(d: int = 64, n: int = 400):
     vdiff = (train.max(0) - vmin).astype(np.float32)
     vdiff[3] = 0  # a constant dimension: the vdiff == 0 branch
     return dict(d=d, n=n, x=x, vmin=vmin, vdiff=vdiff, input_sha=sha(x, vmin, vdiff))
+
+
+# ------------------------------------------------------------------------------- CLI record files
+def write_record_file(path: str, ids, feats: np.ndarray) -> None:
+    """brute_force.cpp's db.bin / querys.bin format:
+    int32 num; num x { int32 idLen; char id[idLen]; int32 dim; float32 feat[dim] }."""
+    with open(path, "wb") as f:
+        np.array([len(ids)], dtype="<i4").tofile(f)
+        for i, s in enumerate(ids):
+            b = s.encode()
+            np.array([len(b)], dtype="<i4").tofile(f)
+            f.write(b)
+            np.array([feats.shape[1]], dtype="<i4").tofile(f)
+            np.ascontiguousarray(feats[i], dtype="<f4").tofile(f)
+
+
+def cli_case():
+    c = flat_case("unit_d128")
+    db_ids = [f"img_{i:06d}" for i in range(c["n"])]
+    q_ids = [f"query_{i:03d}" for i in range(c["nq"])]
+    return dict(db=c["x"], q=c["q"], db_ids=db_ids, q_ids=q_ids)
