@@ -8,6 +8,7 @@
 
 #include "capi_common.cuh"
 #include "pq_kernels.cuh"
+#include "rotate_gemm.cuh"
 #include "topk.cuh"
 
 using namespace b200nn;
@@ -16,8 +17,8 @@ struct b200nn_pq {
     b200nn_ctx* ctx = nullptr;
     int D = 0, K = 0, M = 0, ksub = 0, ds = 0;
     float clamp = 1.0f;
-    bool has_perm = false;
-    DevBuf<float> coarse, coarseT, cb, cbT;
+    bool has_perm = false, has_R = false;
+    DevBuf<float> coarse, coarseT, cb, cbT, rplanes;
     DevBuf<int> perm;
     // rows in insertion order
     long long n = 0, n_groups = 0;
@@ -80,7 +81,8 @@ int pq_init(b200nn_ctx_t ctx, int D, int K, int M, int ksub, const float* coarse
     const int ds = D / M;
     if (!(ds == 1 || ds == 2 || ds == 4 || ds == 8 || ds == 16 || ds == 32))
         B2_FAIL(B200NN_ERR_UNSUPPORTED, "pq_create: D/M must be one of 1,2,4,8,16,32");
-    if (R) B2_FAIL(B200NN_ERR_UNSUPPORTED, "pq_create: dense rotation R is not available in this build (use perm)");
+    if (R && perm) B2_FAIL(B200NN_ERR_INVALID, "pq_create: give either a permutation or a dense rotation R, not both");
+    if (R && !rotate_gemm_supported(D)) B2_FAIL(B200NN_ERR_UNSUPPORTED, "pq_create: the dense rotation (tcgen05 GEMM) needs D % 64 == 0");
     if (perm) {
         std::vector<char> seen(D, 0);
         for (int i = 0; i < D; i++) {
@@ -110,6 +112,13 @@ int pq_init(b200nn_ctx_t ctx, int D, int K, int M, int ksub, const float* coarse
         cudaMemcpyAsync(p->perm.p, perm, sizeof(int) * D, cudaMemcpyHostToDevice, c->stream);
         p->has_perm = true;
     }
+    std::vector<float> packed;
+    if (R) {
+        rotate_gemm_pack_R(R, D, packed);
+        if ((rc = p->rplanes.ensure(packed.size()))) return fail(rc);
+        cudaMemcpyAsync(p->rplanes.p, packed.data(), sizeof(float) * packed.size(), cudaMemcpyHostToDevice, c->stream);
+        p->has_R = true;
+    }
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
         set_last_error("pq_create: device upload failed");
         return fail(B200NN_ERR_CUDA);
@@ -120,7 +129,11 @@ int pq_init(b200nn_ctx_t ctx, int D, int K, int M, int ksub, const float* coarse
 
 // rotate n device rows into dst (or alias src when there is no rotation)
 int rotate_dev(b200nn_pq* p, const float* src, long long n, float* dst, const float** out) {
-    if (p->has_perm) {
+    if (p->has_R) {
+        int rc = launch_rotate_gemm(&p->ctx->c, src, n, p->D, p->rplanes.p, dst);
+        if (rc) return rc;
+        *out = dst;
+    } else if (p->has_perm) {
         int rc = launch_rotate_perm(&p->ctx->c, src, n, p->D, p->perm.p, dst);
         if (rc) return rc;
         *out = dst;
@@ -148,7 +161,7 @@ int add_dev_locked(b200nn_pq* p, const float* x_dev, long long nn, const int* gr
     if ((rc = p->list.reserve((size_t)(p->n + nn), (size_t)p->n, c->stream))) return rc;
     if ((rc = p->group.reserve((size_t)(p->n + nn), (size_t)p->n, c->stream))) return rc;
     const long long chunk = 1 << 18;
-    if (p->has_perm && !already_rotated && (rc = p->ws_x.ensure((size_t)std::min(chunk, nn) * p->D))) return rc;
+    if ((p->has_perm || p->has_R) && !already_rotated && (rc = p->ws_x.ensure((size_t)std::min(chunk, nn) * p->D))) return rc;
     for (long long off = 0; off < nn; off += chunk) {
         const long long cn = std::min(chunk, nn - off);
         const float* xr = x_dev + off * p->D;
@@ -250,7 +263,7 @@ int search_dev_locked(b200nn_pq* p, const float* q_raw_dev, long long nq, int np
     cudaEvent_t* ev = c->events;
     B2_CUDA(cudaEventRecord(ev[0], c->stream));
     const float* qr = nullptr;
-    if (p->has_perm && (rc = p->ws_q.ensure((size_t)nq * p->D))) return rc;
+    if ((p->has_perm || p->has_R) && (rc = p->ws_q.ensure((size_t)nq * p->D))) return rc;
     if ((rc = rotate_dev(p, q_raw_dev, nq, p->ws_q.p, &qr))) return rc;
     B2_CUDA(cudaEventRecord(ev[1], c->stream));
     if (fast_path_ok(p, nprobe, (size_t)k)) {
@@ -261,10 +274,14 @@ int search_dev_locked(b200nn_pq* p, const float* q_raw_dev, long long nq, int np
         if ((rc = launch_lut_build_scan(c, p->M, qr, nq, p->D, p->coarse.p, p->cb.p, p->ws_lut.p))) return rc;
         B2_CUDA(cudaEventRecord(ev[2], c->stream));
         const long long n_gran = (p->n + 63) / 64;
-        const int S = scan_pick_slices(c->sm_count, qgroups, n_gran);
+        int n_full = 0, tail_s = 1;
+        scan_plan(c->sm_count, qgroups, n_gran, &n_full, &tail_s);
+        const int S = tail_s;
         if ((rc = p->ws_keys.ensure((size_t)S * qgroups * QW * k))) return rc;
-        if ((rc = launch_adc_scan_topk(c, p->M, p->codesT.p, p->ws_lut.p, p->n, qgroups, S, k, p->clamp, (uint32_t)id_base,
-                                       p->ws_keys.p)))
+        if (S > 1)  // whole-shard CTAs write slice 0 only: the other slices of those queries stay empty (KEY_MAX)
+            B2_CUDA(cudaMemsetAsync(p->ws_keys.p, 0xFF, (size_t)S * qgroups * QW * k * sizeof(unsigned long long), c->stream));
+        if ((rc = launch_adc_scan_topk(c, p->M, p->codesT.p, p->ws_lut.p, p->n, qgroups, n_full, tail_s, k, p->clamp,
+                                       (uint32_t)id_base, p->ws_keys.p)))
             return rc;
         B2_CUDA(cudaEventRecord(ev[3], c->stream));
         if ((rc = launch_topk_merge(c, p->ws_keys.p, S, nq, k, qgroups * QW * k, out_dist, nullptr, out_id, out_key))) return rc;

@@ -7,6 +7,10 @@
 // __fsub_rn/__fmul_rn/__fadd_rn so nothing is contracted into FMAs; every ADC score is the
 // sequential fp32 sum over m = 0..M-1 starting from 0.0f (IVFOPQ.cpp:302-306).  Codes, LUTs and
 // scores are therefore bit-identical to the reference's.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "pq_kernels.cuh"
 #include "topk.cuh"
 
@@ -235,10 +239,23 @@ __global__ void lut_build_scan_kernel(const float* __restrict__ q, long long nq,
         const float* c = cb + ((long long)m * 256 + j) * DS;
         const float* r = s_res + ql * RS + m * DS;
         float acc = 0.0f;
+        if (DS % 4 == 0) {  // 16-byte loads: codeword row (read-only path) and residual (shared)
 #pragma unroll
-        for (int k = 0; k < DS; k++) {
-            const float t = __fsub_rn(r[k], __ldg(c + k));
-            acc = __fadd_rn(acc, __fmul_rn(t, t));
+            for (int k = 0; k < DS; k += 4) {
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(c + k));
+                const float4 rv = *reinterpret_cast<const float4*>(r + k);
+                float t;
+                t = __fsub_rn(rv.x, cv.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                t = __fsub_rn(rv.y, cv.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                t = __fsub_rn(rv.z, cv.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                t = __fsub_rn(rv.w, cv.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < DS; k++) {
+                const float t = __fsub_rn(r[k], __ldg(c + k));
+                acc = __fadd_rn(acc, __fmul_rn(t, t));
+            }
         }
         out[e] = (qg * QW + ql < nq) ? acc : 0.0f;
     }
@@ -273,16 +290,20 @@ __global__ void lut_build_scan_kernel(const float* __restrict__ q, long long nq,
 // a per-warp staging buffer and are merged into the CTA's sorted per-query list (topk.cuh).
 // Each CTA emits k sorted keys per query; topk_merge_kernel merges the slices.
 // =============================================================================================
-template <int G>
+template <int G, int WARPS_>
 struct ScanCfg {
-    static constexpr int QW = 32 / G;                         // queries per CTA
-    static constexpr int WARPS = 16;
-    static constexpr int STAGE_BLOCKS = (G <= 4) ? 16 : 8;     // blocks (of 4 rows) per ring stage
+    static constexpr int QW = 32 / G;                          // queries per CTA
+    static constexpr int WARPS = WARPS_;
+    static constexpr int STAGE_BLOCKS = (G <= 4) ? 16 : 8;     // blocks (of 4 rows) per ring stage (> G-1 lag)
     static constexpr int STAGE_ROWS = STAGE_BLOCKS * 4;
-    static constexpr int RING_STAGES = 4;
+    static constexpr int RING_STAGES = 3;                      // previous (lagging lane groups) | current | prefetch
     static constexpr int PLANE_RING_BYTES = RING_STAGES * STAGE_ROWS * 4;  // per lane group
     static constexpr int RING_BYTES = G * PLANE_RING_BYTES;                // per warp
-    static constexpr int SB = (G == 1) ? 8 : 16;               // staging records per (warp, query)
+    // staging records per (warp, query): as many as shared memory allows (99 KB beside the LUT)
+    static constexpr int SB = (G == 1) ? 8 : (G == 2 ? 24 : 32);
+    // try to merge once half a buffer is staged (measured: merging much earlier costs more in merges
+    // than the fresher threshold saves in candidates)
+    static constexpr int SOFT = SB / 2;
     static constexpr int STAGING_BYTES = QW * SB * 8;          // per warp
     static constexpr int LIST_BYTES = QW * KP * 8;
     static constexpr int LUT_BYTES = 131072;
@@ -296,30 +317,39 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
     return v;
 }
 
-#define B2_LOOKUP4(S, W)                                                                      \
-    S = __fadd_rn(S, lds_f32_off<0>(__byte_perm(W, basereg, 0x7604)));                          \
+// first look-up of a lane group: S = R*keep + lut[..]  (keep = 0 for lane group 0, which starts the
+// sum at 0.0f, else 1: R*1 + x is R + x with a single rounding, R*0 + x is exactly x)
+#define B2_LOOKUP4(S, R, W)                                                                   \
+    S = __fmaf_rn(R, keep, lds_f32_off<0>(__byte_perm(W, basereg, 0x7604)));                    \
     S = __fadd_rn(S, lds_f32_off<128>(__byte_perm(W, basereg, 0x7614)));                        \
     S = __fadd_rn(S, lds_f32_off<65536>(__byte_perm(W, basereg, 0x7624)));                      \
     S = __fadd_rn(S, lds_f32_off<65536 + 128>(__byte_perm(W, basereg, 0x7634)));
 
-template <int G>
-__global__ void __launch_bounds__(ScanCfg<G>::WARPS * 32, 1)
+// Work decomposition: one CTA per (query group, row slice).  The first n_full query groups are
+// scanned whole by one CTA each (whole waves of one-CTA-per-SM); the remaining groups (the partial
+// last wave) are split into tail_s row slices so that the last wave also fills the machine.  Every
+// (query, CTA) pair pays a top-k warm-up of ~k(1 + ln(rows/k)) insertions, so slices are used only
+// where they buy balance.
+template <int G, int WARPS_>
+__global__ void __launch_bounds__(WARPS_ * 32, 1)
 adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                      const float* __restrict__ lut_scan,    // [qgroups][32768]
                      long long n_rows,                      // valid rows of this shard
                      long long n_granules,                  // ceil(n_rows / 64)
-                     int n_slices, int k, float clamp, uint32_t id_base,
+                     int n_full, int tail_s, int k, float clamp, uint32_t id_base,
                      unsigned long long* __restrict__ out_keys,  // [slice][qgroups*QW][k]
                      long long q_stride_total,                   // qgroups*QW
                      int* __restrict__ err_flag) {
-    using C = ScanCfg<G>;
+    using C = ScanCfg<G, WARPS_>;
     constexpr int QW = C::QW;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int h = lane / QW, ql = lane - h * QW;
     const bool last_group = (h == G - 1);
-    const long long qg = blockIdx.x;
-    const int slice = blockIdx.y;
+    long long qg;
+    int slice, n_slices;
+    if ((int)blockIdx.x < n_full) { qg = blockIdx.x; slice = 0; n_slices = 1; }
+    else { const int idx = (int)blockIdx.x - n_full; qg = n_full + idx / tail_s; slice = idx % tail_s; n_slices = tail_s; }
 
     // ---- carve shared memory: LUT at a 64 KB aligned window address, the rest around it ----
     const uint32_t base = smem_u32(dyn_smem);
@@ -336,19 +366,18 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     for (int i = 0; i < C::WARPS; i++) { const uint32_t p = carve(C::RING_BYTES); if (i == w) ring_w = p; }
     const uint32_t lists = carve(C::LIST_BYTES);
     for (int i = 0; i < C::WARPS; i++) { const uint32_t p = carve(C::STAGING_BYTES); if (i == w) staging_w = p; }
-    const uint32_t misc = carve(1024);
+    const uint32_t misc = carve(2048);
     if (!ok) { if (threadIdx.x == 0) atomicExch(err_flag, 1); return; }
-    // misc: [0,8) lut barrier | [64, 64+WARPS*32) per-warp full barriers | [640, 640+QW*8) tau keys | [896, 896+QW*4) locks
+    // misc: [0,8) lut barrier | [64, 64+WARPS*32) per-warp full barriers | [1024, +QW*8) tau keys | [1536, +QW*4) locks
     const uint32_t lut_bar = misc;
     const uint32_t full_bar = misc + 64 + (uint32_t)w * 32;
     unsigned char* generic_base = dyn_smem - base;  // generic pointer of shared-window address 0
-    volatile unsigned long long* tau_key = (volatile unsigned long long*)(generic_base + misc + 640);
-    int* locks = (int*)(generic_base + misc + 896);
+    volatile unsigned long long* tau_key = (volatile unsigned long long*)(generic_base + misc + 1024);
+    int* locks = (int*)(generic_base + misc + 1536);
 
     // ---- this warp's stream of rows ----
     const long long g_lo = (n_granules * slice) / n_slices, g_hi = (n_granules * (slice + 1)) / n_slices;
-    constexpr int GRAN_PER_STAGE_NUM = C::STAGE_ROWS;  // rows per stage (64 or 32)
-    const long long stages_total = (g_hi - g_lo) * (64 / GRAN_PER_STAGE_NUM);
+    const long long stages_total = (g_hi - g_lo) * (64 / C::STAGE_ROWS);
     const long long st_per_warp = (stages_total + C::WARPS - 1) / C::WARPS;
     const long long st_lo = min(stages_total, (long long)w * st_per_warp), st_hi = min(stages_total, st_lo + st_per_warp);
     const int n_st = (int)(st_hi - st_lo);
@@ -377,8 +406,8 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     // ---- code prefetch ----
     // stage s of this warp = rows [row0 + s*STAGE_ROWS, +STAGE_ROWS); plane h of it is STAGE_ROWS
     // consecutive words inside granule (row/64), plane h.
-    auto issue_stage = [&](int s) {
-        const uint32_t bar = full_bar + 8 * (s & (C::RING_STAGES - 1));
+    auto issue_stage = [&](int s, int slot) {
+        const uint32_t bar = full_bar + 8 * slot;
         if (lane == 0) mbar_arrive_expect_tx(bar, G * C::STAGE_ROWS * 4);
         __syncwarp();
         if (lane < G) {
@@ -386,93 +415,121 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
             const long long gran = row >> 6;
             const int within = (int)(row & 63);
             const uint32_t* src = codesT + (gran * G + lane) * 64 + within;
-            const uint32_t dst = ring_w + (uint32_t)lane * C::PLANE_RING_BYTES +
-                                 (uint32_t)(s & (C::RING_STAGES - 1)) * (C::STAGE_ROWS * 4);
+            const uint32_t dst = ring_w + (uint32_t)lane * C::PLANE_RING_BYTES + (uint32_t)slot * (C::STAGE_ROWS * 4);
             tma_load_1d(dst, src, C::STAGE_ROWS * 4, bar);
         }
     };
-    if (n_st > 0) issue_stage(0);
-    if (n_st > 1) issue_stage(1);
+    if (n_st > 0) issue_stage(0, 0);
 
     mbar_wait(lut_bar, 0);  // LUT resident
 
     const uint32_t basereg = lut + (uint32_t)lane * 4u;
     const uint32_t plane = ring_w + (uint32_t)h * C::PLANE_RING_BYTES;
     const uint32_t my_staging = staging_w + (uint32_t)ql * (C::SB * 8);
+    const float keep = (h == 0) ? 0.0f : 1.0f;
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    // tau = prefilter threshold on the RAW score: the k-th best distance, or +inf while the list
-    // is not full or while the clamp value itself would still qualify (clamped scores tie at
-    // `clamp`, the record comparison below then decides).  -inf on lanes that own no final score.
+    // Per-lane threshold state (meaningful on the last lane group, which owns final scores):
+    //   tkey : the query's k-th best record so far (KEY_MAX while the list is not full)
+    //   tsc  : its score (+inf while not full)
+    //   tau  : prefilter on the RAW score: tsc, or +inf while the clamp value itself would still
+    //          qualify (clamped scores tie at `clamp`; the record comparison then decides);
+    //          -inf on lanes that own no final score.
     unsigned long long tkey = KEY_MAX;
+    float tsc = __int_as_float(0x7f800000);
     float tau = last_group ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
     int cnt = 0;  // staged records (last group lanes)
     auto refresh_tau = [&]() {
         if (last_group) {
             tkey = tau_key[ql];
-            const float t = tau_f32_of(tkey);
-            tau = (clamp <= t) ? __int_as_float(0x7f800000) : t;
+            tsc = tau_f32_of(tkey);
+            tau = (clamp <= tsc) ? __int_as_float(0x7f800000) : tsc;
         }
     };
     // byte offset of this lane's current block inside its plane ring (block index = Bg - h)
-    uint32_t coff = (uint32_t)((-h * 16) & (C::PLANE_RING_BYTES - 1));
+    uint32_t coff = (h == 0) ? 0u : (uint32_t)(C::PLANE_RING_BYTES - h * 16);
+    // 32-bit row bookkeeping for the candidate path: valid relative rows are [0, nrel)
+    const uint32_t nrel = (uint32_t)max(0LL, min((long long)nblocks * 4, n_rows - row0));
+    const uint32_t idbase = id_base + (uint32_t)row0;
 
-    auto rare_path = [&](int Bg) {
-        // Bg = block counter of lane group 0; this lane's block is Bg - h.
-        const int Bh = Bg - h;
-        if (last_group && Bh >= 0 && Bh < nblocks) {
-            const long long r = row0 + (long long)Bh * 4;
-            const float sc[4] = {o0, o1, o2, o3};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float s = sc[j];
-                s = clamp < s ? clamp : s;  // std::min(score, threhold-initialised slot), IVFOPQ.cpp:410
-                const unsigned long long key = make_key(f32_orderable(s), id_base + (uint32_t)(r + j));
-                if (key < tkey && r + j < n_rows) {
-                    sts64(my_staging + (uint32_t)cnt * 8u, key);
-                    cnt++;
-                }
-            }
-        }
-        __syncwarp();
-        unsigned need = __ballot_sync(0xffffffffu, cnt > C::SB - 4);
+    // flush the staging buffers of the lanes in `need` (lane mask) into the CTA lists
+    auto flush_lanes = [&](unsigned need, bool blocking) {
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
             const int qsel = src - (G - 1) * QW;
             const int nb = __shfl_sync(0xffffffffu, cnt, src);
-            warp_flush(lists + (uint32_t)qsel * (KP * 8), locks + qsel, tau_key + qsel,
-                       staging_w + (uint32_t)qsel * (C::SB * 8), nb, k);
-            if (lane == src) cnt = 0;
+            int got = 1;
+            if (!blocking) {  // try-lock: keep scanning if another warp is merging this query
+                if (lane == 0) got = (atomicCAS(locks + qsel, 0, 1) == 0);
+                got = __shfl_sync(0xffffffffu, got, 0);
+                if (got && lane == 0) __threadfence_block();
+            }
+            if (got) {
+                warp_flush(lists + (uint32_t)qsel * (KP * 8), locks + qsel, tau_key + qsel,
+                           staging_w + (uint32_t)qsel * (C::SB * 8), nb, k, /*lock_held=*/!blocking);
+                if (lane == src) { cnt = 0; refresh_tau(); }
+            }
         }
-        refresh_tau();
+    };
+
+    auto rare_path = [&](int Bg, float mn) {
+        // Bg = block counter of lane group 0; this lane's block is Bg - h.  Only lanes of the last
+        // lane group can satisfy mn <= tau (tau = -inf elsewhere).
+        if (mn <= tau) {
+            const uint32_t rel0 = (uint32_t)(Bg - h) * 4u;
+            const float sc[4] = {o0, o1, o2, o3};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float s = sc[j];
+                s = clamp < s ? clamp : s;  // std::min(score, threhold-initialised slot), IVFOPQ.cpp:410
+                if (s <= tsc && rel0 + j < nrel) {
+                    // scores are sums of squares (>= +0): the orderable form is just the sign bit set
+                    const uint32_t ord = __float_as_uint(s) | 0x80000000u, id = idbase + rel0 + j;
+                    if (s < tsc || make_key(ord, id) < tkey) {
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(my_staging + (uint32_t)cnt * 8u), "r"(id), "r"(ord) : "memory");
+                        cnt++;
+                    }
+                }
+            }
+        }
+        const unsigned soft = __ballot_sync(0xffffffffu, cnt >= C::SOFT);
+        if (soft) {
+            const unsigned hard = __ballot_sync(0xffffffffu, cnt > C::SB - 4);
+            if (hard) flush_lanes(hard, true);
+            else flush_lanes(soft, false);
+        }
     };
 
     auto block_body = [&](int Bg) {
         const uint4 cw = lds128(plane + coff);
-        coff = (coff + 16u) & (uint32_t)(C::PLANE_RING_BYTES - 1);
-        float s0, s1, s2, s3;
+        coff += 16u;
+        if (coff == (uint32_t)C::PLANE_RING_BYTES) coff = 0u;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
         if (G > 1) {
-            s0 = __shfl_up_sync(0xffffffffu, o0, QW);
-            s1 = __shfl_up_sync(0xffffffffu, o1, QW);
-            s2 = __shfl_up_sync(0xffffffffu, o2, QW);
-            s3 = __shfl_up_sync(0xffffffffu, o3, QW);
-            if (h == 0) { s0 = 0.f; s1 = 0.f; s2 = 0.f; s3 = 0.f; }
-        } else {
-            s0 = 0.f; s1 = 0.f; s2 = 0.f; s3 = 0.f;
+            r0 = __shfl_up_sync(0xffffffffu, o0, QW);
+            r1 = __shfl_up_sync(0xffffffffu, o1, QW);
+            r2 = __shfl_up_sync(0xffffffffu, o2, QW);
+            r3 = __shfl_up_sync(0xffffffffu, o3, QW);
         }
-        B2_LOOKUP4(s0, cw.x)
-        B2_LOOKUP4(s1, cw.y)
-        B2_LOOKUP4(s2, cw.z)
-        B2_LOOKUP4(s3, cw.w)
+        float s0, s1, s2, s3;
+        B2_LOOKUP4(s0, r0, cw.x)
+        B2_LOOKUP4(s1, r1, cw.y)
+        B2_LOOKUP4(s2, r2, cw.z)
+        B2_LOOKUP4(s3, r3, cw.w)
         o0 = s0; o1 = s1; o2 = s2; o3 = s3;
         const float mn = fminf(fminf(s0, s1), fminf(s2, s3));
-        if (__any_sync(0xffffffffu, mn <= tau)) rare_path(Bg);
+        if (__any_sync(0xffffffffu, mn <= tau)) rare_path(Bg, mn);
     };
 
-    int Bg = 0;
+    int Bg = 0, slot = 0;
+    uint32_t phases = 0;  // bit s = parity to wait for on ring slot s
     for (int st = 0; st < n_st; st++) {
-        if (st + 2 < n_st) issue_stage(st + 2);
-        mbar_wait(full_bar + 8 * (st & (C::RING_STAGES - 1)), (uint32_t)(st / C::RING_STAGES) & 1u);
+        const int next = (slot == C::RING_STAGES - 1) ? 0 : slot + 1;
+        // the slot after the current one held stage st-2, which every lane group has left
+        if (st + 1 < n_st) issue_stage(st + 1, next);
+        mbar_wait(full_bar + 8 * slot, (phases >> slot) & 1u);
+        phases ^= 1u << slot;
+        slot = next;
         refresh_tau();
 #pragma unroll 4
         for (int bb = 0; bb < C::STAGE_BLOCKS; bb++, Bg++) block_body(Bg);
@@ -480,17 +537,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     for (int d = 0; d < G - 1; d++, Bg++) block_body(Bg);  // drain the lane-group pipeline
 
     // ---- flush what is still staged, then emit the CTA's sorted lists ----
-    {
-        unsigned need = __ballot_sync(0xffffffffu, last_group && cnt > 0);
-        while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const int qsel = src - (G - 1) * QW;
-            const int nb = __shfl_sync(0xffffffffu, cnt, src);
-            warp_flush(lists + (uint32_t)qsel * (KP * 8), locks + qsel, tau_key + qsel,
-                       staging_w + (uint32_t)qsel * (C::SB * 8), nb, k);
-        }
-    }
+    flush_lanes(__ballot_sync(0xffffffffu, last_group && cnt > 0), true);
     __syncthreads();
     for (int i = threadIdx.x; i < QW * k; i += blockDim.x) {
         const int qq = i / k, j = i - qq * k;
@@ -699,48 +746,66 @@ int launch_lut_build_scan(Ctx* ctx, int M, const float* q, long long nq, int D, 
 
 int scan_queries_per_cta(int M) { return M >= 4 ? 128 / M : 0; }
 
-// number of database slices: fill whole waves of one-CTA-per-SM, keep slices long
-int scan_pick_slices(int sm_count, long long qgroups, long long n_granules) {
-    if (qgroups <= 0) return 1;
-    int best_s = 1;
-    double best_eff = 0.0;
-    for (int s = 1; s <= 64; s++) {
-        if (s > 1 && n_granules / s < 64) break;  // >= 4096 rows per CTA
-        const double ctas = (double)qgroups * s;
-        const double waves = ctas / sm_count;
-        const double eff = waves / (double)(long long)(waves + 0.999999);
-        if (eff > best_eff + 0.02) { best_eff = eff; best_s = s; }
-        if (best_eff > 0.97) break;
+// Work plan of the scan (see adc_scan_topk_kernel): n_full query groups get one whole-shard CTA each
+// (full waves of one-CTA-per-SM); the groups of the partial last wave are split into tail_s row slices.
+void scan_plan(int sm_count, long long qgroups, long long n_granules, int* n_full, int* tail_s) {
+    const long long waves = qgroups / sm_count;
+    const long long rem = qgroups - waves * sm_count;
+    *n_full = (int)(waves * sm_count);
+    long long s = 1;
+    if (rem > 0) {
+        s = sm_count / rem;
+        const long long max_s = std::max<long long>(1, n_granules / 16);  // >= 1024 rows per slice
+        if (s > max_s) s = max_s;
+        if (s > 64) s = 64;
+        if (s < 1) s = 1;
     }
-    return best_s;
+    *tail_s = (int)s;
 }
 
-template <int G>
-static int scan_dispatch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
-                         int n_slices, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
-    using C = ScanCfg<G>;
+static int scan_warps_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200NN_SCAN_WARPS");
+        v = (e && atoi(e) == 24) ? 24 : 16;
+    }
+    return v;
+}
+
+template <int G, int WARPS_>
+static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
+                       int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
+    using C = ScanCfg<G, WARPS_>;
     static bool attr_set = false;
     if (!attr_set) {
-        B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
     const long long n_gran = (n_rows + 63) / 64;
-    dim3 grid((unsigned)qgroups, (unsigned)n_slices);
-    adc_scan_topk_kernel<G><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
-        codesT, lut_scan, n_rows, n_gran, n_slices, k, clamp, id_base, out_keys, qgroups * C::QW, ctx->d_err);
+    const unsigned grid = (unsigned)(n_full + (qgroups - n_full) * tail_s);
+    adc_scan_topk_kernel<G, WARPS_><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
+        codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, ctx->d_err);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;
 }
 
+template <int G>
+static int scan_dispatch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
+                         int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
+    if (G == 4 && scan_warps_variant() == 24)
+        return scan_launch<G, 24>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
+    return scan_launch<G, 16>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
+}
+
 int launch_adc_scan_topk(Ctx* ctx, int M, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
-                         int n_slices, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
+                         int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
     if (k < 1 || k > KP) B2_FAIL(-4, "fused ADC top-k supports 1 <= k <= 128");
     switch (M) {
-        case 4: return scan_dispatch<1>(ctx, codesT, lut_scan, n_rows, qgroups, n_slices, k, clamp, id_base, out_keys);
-        case 8: return scan_dispatch<2>(ctx, codesT, lut_scan, n_rows, qgroups, n_slices, k, clamp, id_base, out_keys);
-        case 16: return scan_dispatch<4>(ctx, codesT, lut_scan, n_rows, qgroups, n_slices, k, clamp, id_base, out_keys);
-        case 32: return scan_dispatch<8>(ctx, codesT, lut_scan, n_rows, qgroups, n_slices, k, clamp, id_base, out_keys);
+        case 4: return scan_dispatch<1>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
+        case 8: return scan_dispatch<2>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
+        case 16: return scan_dispatch<4>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
+        case 32: return scan_dispatch<8>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
         default: B2_FAIL(-4, "fast ADC scan supports M in {4, 8, 16, 32}");
     }
 }

@@ -1,0 +1,229 @@
+// rotate_gemm.cu -- a1 as a dense rotation: Y[n,D] = X[n,D] * R^T on the 5th-generation tensor
+// cores (tcgen05.mma kind::tf32, accumulators in TMEM), at ~fp32 accuracy through an error-free
+// split of both operands ("3xTF32"):
+//     x = x0 + x1 + x2   (each part has <= 11 significant bits: exactly representable in TF32)
+//     R = r0 + r1        (pre-split once per model on the host)
+//     y = x2*r0 + x1*r1 + x1*r0 + x0*r1 + x0*r0        (small terms first)
+// Every product of TF32-exact operands is exact in fp32; the only roundings are the fp32
+// accumulations in TMEM.  For a PERMUTATION matrix (r1 = 0, entries 0/1) every partial sum is
+// exactly representable, so the result is bit-identical to the gather of IVFOPQ::reorder
+// (opq/src/IVFOPQ.cpp:424-439) -- tests/test_rotate_gemm_gpu.py checks that on the device.
+//
+// Tile: one CTA computes 128 rows x NB (64|128) output columns; K is walked in chunks of 32.
+//   A (rows of X): read with 16-byte global loads, split in registers, written as three K-major
+//      no-swizzle "core matrix" tiles (8 rows x 16 bytes, LBO = K-direction, SBO = row-group direction).
+//   B (R parts):   pre-arranged in global memory in the same canonical order, so a chunk is ONE
+//      contiguous TMA bulk copy (cp.async.bulk -> UBLKCP) completing on an mbarrier.
+//   MMA: thread 0 issues 4 k-steps x 5 products of tcgen05.mma (M=128, N=NB, K=8) per chunk and
+//      tcgen05.commit's to the barrier that frees the double-buffered stage.
+//   Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> 16-byte global stores.
+#include <stdint.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "rotate_gemm.cuh"
+
+namespace b200nn {
+
+constexpr int RG_M = 128;   // rows per tile (= TMEM lanes)
+constexpr int RG_KC = 32;   // K elements per chunk (4 MMA k-steps of 8)
+constexpr int RG_THREADS = 128;
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | swizzle none
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+template <int NB>
+__global__ void __launch_bounds__(RG_THREADS, 1)
+rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int D, const float* __restrict__ bplanes,
+                          float* __restrict__ y) {
+    constexpr uint32_t A_PLANE = RG_M * RG_KC * 4;       // 16 KB
+    constexpr uint32_t B_PLANE = NB * RG_KC * 4;         // 8 / 16 KB
+    constexpr uint32_t A_LBO = RG_M * 16, B_LBO = NB * 16, SBO = 128;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t sA = s_base;                            // [2 stages][3 planes][A_PLANE]
+    const uint32_t sB = sA + 2 * 3 * A_PLANE;              // [2 stages][2 planes][B_PLANE]
+    const uint32_t bars = sB + 2 * 2 * B_PLANE;            // b_full[2], stage_free[2], accum_full, tmem slot
+    const uint32_t b_full = bars, stage_free = bars + 16, accum_full = bars + 32, tmem_slot = bars + 48;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nblk = blockIdx.x;                           // output column block (fastest: shares X rows in L2)
+    const long long tile = blockIdx.y;
+    const int nchunks = D / RG_KC;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)NB) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(b_full, 1); mbar_init(b_full + 8, 1);
+        mbar_init(stage_free, 1); mbar_init(stage_free + 8, 1);
+        mbar_init(accum_full, 1);
+        mbar_fence_init();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(RG_M >> 4) << 24);
+
+    const long long row = tile * RG_M + tid;
+    const bool valid = row < n;
+    const float* xrow = x + row * D;
+    const uint32_t a_row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+
+    for (int kc = 0; kc < nchunks; kc++) {
+        const int st = kc & 1, use = kc >> 1;
+        if (kc >= 2) mbar_wait(stage_free + 8 * st, (uint32_t)(use - 1) & 1u);  // MMAs of chunk kc-2 have drained this stage
+        if (tid == 0) {
+            mbar_arrive_expect_tx(b_full + 8 * st, 2 * B_PLANE);
+            tma_load_1d(sB + (uint32_t)st * 2 * B_PLANE, bplanes + ((size_t)nblk * nchunks + kc) * (2 * NB * RG_KC), 2 * B_PLANE,
+                        b_full + 8 * st);
+        }
+        const uint32_t a0 = sA + (uint32_t)st * 3 * A_PLANE + a_row_off;
+#pragma unroll
+        for (int c = 0; c < RG_KC / 4; c++) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) v = __ldg(reinterpret_cast<const float4*>(xrow + kc * RG_KC + c * 4));
+            const float h0 = tf32_trunc(v.x), h1 = tf32_trunc(v.y), h2 = tf32_trunc(v.z), h3 = tf32_trunc(v.w);
+            const float r0 = __fsub_rn(v.x, h0), r1 = __fsub_rn(v.y, h1), r2 = __fsub_rn(v.z, h2), r3 = __fsub_rn(v.w, h3);
+            const float m0 = tf32_trunc(r0), m1 = tf32_trunc(r1), m2 = tf32_trunc(r2), m3 = tf32_trunc(r3);
+            const float l0 = tf32_trunc(__fsub_rn(r0, m0)), l1 = tf32_trunc(__fsub_rn(r1, m1)), l2 = tf32_trunc(__fsub_rn(r2, m2)),
+                        l3 = tf32_trunc(__fsub_rn(r3, m3));
+            const uint32_t o = a0 + (uint32_t)c * A_LBO;
+            sts128(o, h0, h1, h2, h3);
+            sts128(o + A_PLANE, m0, m1, m2, m3);
+            sts128(o + 2 * A_PLANE, l0, l1, l2, l3);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(b_full + 8 * st, (uint32_t)use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t A = sA + (uint32_t)st * 3 * A_PLANE, B = sB + (uint32_t)st * 2 * B_PLANE;
+#pragma unroll
+            for (int s = 0; s < RG_KC / 8; s++) {
+                const uint32_t ak = (uint32_t)s * 2 * A_LBO, bk = (uint32_t)s * 2 * B_LBO;
+                const uint64_t da0 = umma_desc_kmajor(A + ak, A_LBO, SBO), da1 = umma_desc_kmajor(A + A_PLANE + ak, A_LBO, SBO),
+                               da2 = umma_desc_kmajor(A + 2 * A_PLANE + ak, A_LBO, SBO);
+                const uint64_t db0 = umma_desc_kmajor(B + bk, B_LBO, SBO), db1 = umma_desc_kmajor(B + B_PLANE + bk, B_LBO, SBO);
+                umma_tf32(tmem_base, da2, db0, idesc, (kc | s) != 0);  // first MMA of the tile overwrites the accumulator
+                umma_tf32(tmem_base, da1, db1, idesc, 1);
+                umma_tf32(tmem_base, da1, db0, idesc, 1);
+                umma_tf32(tmem_base, da0, db1, idesc, 1);
+                umma_tf32(tmem_base, da0, db0, idesc, 1);
+            }
+            umma_commit(stage_free + 8 * st);
+            if (kc == nchunks - 1) umma_commit(accum_full);
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers -> global ----
+    mbar_wait(accum_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* yrow = y + row * D + (size_t)nblk * NB;
+#pragma unroll
+    for (int c0 = 0; c0 < NB; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(yrow + c0 + i) =
+                    make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)NB) : "memory");
+}
+
+// ---- host ----
+int rotate_gemm_nblock(int D) { return (D % 128 == 0) ? 128 : 64; }
+
+bool rotate_gemm_supported(int D) { return D >= 64 && D % 64 == 0; }
+
+// R [D,D] row-major (y = R x) -> two TF32-exact parts in the canonical K-major core-matrix order,
+// one contiguous block per (output block, K chunk): [nblk][kc][part][ (k/4) | (n/8) | n%8 | k%4 ]
+void rotate_gemm_pack_R(const float* R, int D, std::vector<float>& out) {
+    const int NB = rotate_gemm_nblock(D), nblocks = D / NB, nchunks = D / RG_KC;
+    out.assign((size_t)D * D * 2, 0.0f);
+    auto trunc = [](float v) {
+        union { float f; uint32_t u; } c;
+        c.f = v;
+        c.u &= 0xFFFFE000u;
+        return c.f;
+    };
+    for (int nb = 0; nb < nblocks; nb++)
+        for (int kc = 0; kc < nchunks; kc++) {
+            float* blk = out.data() + ((size_t)nb * nchunks + kc) * (2 * NB * RG_KC);
+            for (int nl = 0; nl < NB; nl++)
+                for (int kl = 0; kl < RG_KC; kl++) {
+                    const float v = R[(size_t)(nb * NB + nl) * D + kc * RG_KC + kl];
+                    const float r0 = trunc(v), r1 = trunc(v - r0);
+                    const size_t off = (size_t)(kl / 4) * (NB * 4) + (size_t)(nl / 8) * 32 + (nl % 8) * 4 + (kl % 4);
+                    blk[off] = r0;
+                    blk[(size_t)NB * RG_KC + off] = r1;
+                }
+        }
+}
+
+int launch_rotate_gemm(Ctx* ctx, const float* x, long long n, int D, const float* bplanes, float* y) {
+    if (n <= 0) return 0;
+    if (!rotate_gemm_supported(D)) B2_FAIL(-4, "dense rotation needs D % 64 == 0");
+    const int NB = rotate_gemm_nblock(D);
+    const size_t smem = 2 * 3 * (size_t)RG_M * RG_KC * 4 + 2 * 2 * (size_t)NB * RG_KC * 4 + 64;
+    const long long n_tiles = (n + RG_M - 1) / RG_M;
+    // gridDim.y limit is 65535: fold the row tiles into several launches
+    const long long max_tiles = 65535;
+    for (long long t0 = 0; t0 < n_tiles; t0 += max_tiles) {
+        const long long tiles = std::min<long long>(max_tiles, n_tiles - t0);
+        const long long rows0 = t0 * RG_M, rows = std::min<long long>(n - rows0, tiles * RG_M);
+        dim3 g((unsigned)(D / NB), (unsigned)tiles);
+        if (NB == 128) {
+            B2_CUDA(cudaFuncSetAttribute(rotate_gemm_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rotate_gemm_tf32x3_kernel<128><<<g, RG_THREADS, smem, ctx->stream>>>(x + rows0 * D, rows, D, bplanes, y + rows0 * D);
+        } else {
+            B2_CUDA(cudaFuncSetAttribute(rotate_gemm_tf32x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rotate_gemm_tf32x3_kernel<64><<<g, RG_THREADS, smem, ctx->stream>>>(x + rows0 * D, rows, D, bplanes, y + rows0 * D);
+        }
+        ctx->launches++;
+    }
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200nn

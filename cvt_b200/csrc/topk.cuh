@@ -29,11 +29,16 @@ __device__ __forceinline__ void warp_list_merge(uint32_t L_addr, uint32_t cand_a
     }
     const unsigned long long c = lane < nb ? lds64(cand_addr + (uint32_t)lane * 8u) : KEY_MAX;
     int pc = 0;
-    for (int j = 0; j < nb; j++) {
-        const unsigned long long cj = lds64(cand_addr + (uint32_t)j * 8u);  // broadcast read
+    for (int j0 = 0; j0 < nb; j0 += 4) {  // 4 broadcast reads in flight per step
+        unsigned long long cj[4];
 #pragma unroll
-        for (int t = 0; t < KP / 32; t++) pl[t] += (cj < l[t]) ? 1 : 0;
-        pc += (cj < c) ? 1 : 0;
+        for (int u = 0; u < 4; u++) cj[u] = (j0 + u < nb) ? lds64(cand_addr + (uint32_t)(j0 + u) * 8u) : KEY_MAX;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int t = 0; t < KP / 32; t++) pl[t] += (cj[u] < l[t]) ? 1 : 0;
+            pc += (cj[u] < c) ? 1 : 0;
+        }
     }
     // number of list entries < c (lower bound in the sorted list; KP is a power of two)
     int pos = 0;
@@ -55,10 +60,13 @@ __device__ __forceinline__ void warp_list_merge(uint32_t L_addr, uint32_t cand_a
 // Locked flush of a staging buffer into the CTA list of one query; publishes the new threshold
 // *tau_key = the k-th best record (KEY_MAX while the list holds fewer than k records).
 __device__ __forceinline__ void warp_flush(uint32_t L_addr, int* lock, volatile unsigned long long* tau_key,
-                                           uint32_t cand_addr, int nb, int k) {
-    if (nb <= 0) return;  // warp-uniform
+                                           uint32_t cand_addr, int nb, int k, bool lock_held = false) {
     const int lane = threadIdx.x & 31;
-    if (lane == 0) {
+    if (nb <= 0) {  // warp-uniform
+        if (lock_held && lane == 0) atomicExch(lock, 0);
+        return;
+    }
+    if (lane == 0 && !lock_held) {
         while (atomicCAS(lock, 0, 1) != 0) {
         }
         __threadfence_block();

@@ -40,6 +40,17 @@ ORC_API void orc_opq_reorder(const float* x, int64_t n, int D, const int32_t* pe
         for (int i = 0; i < D; i++) y[r * D + i] = x[r * D + perm[i]];
 }
 
+/* Dense-rotation extension (the reference's "rotation" is always a permutation): y = R x with a
+ * sequential fp32 dot product per output, R row-major [D][D].  Used to bound the tcgen05 GEMM. */
+ORC_API void orc_opq_rotate_dense(const float* x, int64_t n, int D, const float* R, float* y) {
+    for (int64_t r = 0; r < n; r++)
+        for (int i = 0; i < D; i++) {
+            float acc = 0.0f;
+            for (int j = 0; j < D; j++) acc += R[(int64_t)i * D + j] * x[r * D + j];
+            y[r * D + i] = acc;
+        }
+}
+
 /* Squared distance exactly as written at IVFOPQ.cpp:117-122 / :147-154 / :283-288:
  * acc = 0.0f; for k ascending { tmp = a[k]-b[k]; acc += tmp*tmp; }  (two roundings per term). */
 static inline float sqdist_seq(const float* a, const float* b, int d) {

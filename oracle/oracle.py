@@ -61,6 +61,13 @@ def opq_reorder(x, perm):
     return y
 
 
+def opq_rotate_dense(x, R):
+    x, R = _f32(x), _f32(R)
+    y = np.empty_like(x)
+    lib().orc_opq_rotate_dense(_p(x), C.c_int64(x.shape[0]), C.c_int(x.shape[1]), _p(R), _p(y))
+    return y
+
+
 def opq_coarse_assign(x_rot, coarse):
     x_rot, coarse = _f32(x_rot), _f32(coarse)
     out = np.empty(x_rot.shape[0], dtype=np.int32)

@@ -22,7 +22,7 @@ t0 = time.time(); idx.add(db); print(f"add {n} rows: {time.time()-t0:.2f}s", flu
 qd = torch.from_numpy(q).cuda()
 od = torch.empty((B, k), dtype=torch.float32, device="cuda")
 oi = torch.empty((B, k), dtype=torch.int64, device="cuda")
-for it in range(6):
+for it in range(5):
     idx.search_dev(qd.data_ptr(), B, k, 1, od.data_ptr(), oi.data_ptr())
     ctx.synchronize()
     t = idx.last_timing()
