@@ -1,6 +1,7 @@
 // capi_flat.cu -- C ABI of the exact flat index: hnswlib::BruteforceSearch<float|int> drop-in
 // (brute_force_search/src/brutoforce.hpp:8-136; identical copy hnsw_sifts_retrieval/hnswlib/brutoforce.h).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <numeric>
@@ -10,6 +11,7 @@
 #include "capi_common.cuh"
 #include "flat_kernels.cuh"
 #include "topk.cuh"
+#include "u8_scan_tc.cuh"
 
 using namespace b200nn;
 
@@ -24,6 +26,10 @@ struct b200nn_flat {
     bool ranks_valid = false;
     DevBuf<uint32_t> rank;                      // rank of each row's label
     DevBuf<unsigned long long> label_sorted;    // rank -> label
+    // tensor-core scan layout of u8 rows (metric 2): canonical 256-row tiles + |x|^2
+    long long tc_rows = -1;
+    DevBuf<unsigned char> xcan;
+    DevBuf<int> xnorm;
     DevBuf<unsigned char> ws_q;
     DevBuf<unsigned long long> ws_keys, ws_id;
     DevBuf<float> ws_dist;
@@ -85,6 +91,23 @@ int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, vo
     if (k < 1 || k > (size_t)KP) B2_FAIL(B200NN_ERR_UNSUPPORTED, "flat_search: k must be in [1, 128]");
     int rc;
     if ((rc = ensure_ranks(p))) return rc;
+    if (p->metric == 2 && u8_scan_tc_supported((int)p->dim, (int)k) && !getenv("B200NN_NO_TC_U8")) {
+        // u8 x u8 -> s32 contraction on the tensor cores (tcgen05 kind::i8) with the fused top-k epilogue
+        if (p->tc_rows != (long long)p->n) {
+            const long long n_pad = std::max<long long>(256, ((long long)p->n + 255) / 256 * 256);
+            if ((rc = p->xcan.ensure((size_t)n_pad * p->dim)) || (rc = p->xnorm.ensure((size_t)n_pad))) return rc;
+            if ((rc = launch_u8_rows_to_canonical(c, p->data.p, (long long)p->n, (int)p->dim, p->xcan.p, p->xnorm.p, n_pad))) return rc;
+            p->tc_rows = (long long)p->n;
+        }
+        const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, (long long)p->n);
+        if ((rc = p->ws_keys.ensure((size_t)S * nq * k))) return rc;
+        if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, p->rank.p, (long long)p->n, (int)p->dim, (const unsigned char*)q_dev,
+                                    (long long)nq, S, (int)k, p->ws_keys.p)))
+            return rc;
+        if ((rc = launch_topk_merge(c, p->ws_keys.p, S, (long long)nq, (int)k, (long long)(nq * k), nullptr, (int*)out_dist, out_label, nullptr)))
+            return rc;
+        return launch_rank_to_label(c, out_label, (long long)(nq * k), p->label_sorted.p);
+    }
     const int S = flat_pick_slices(c->sm_count, (long long)nq, (long long)p->n);
     if ((rc = p->ws_keys.ensure((size_t)S * nq * k))) return rc;
     if ((rc = launch_flat_scan(c, p->metric, p->order, p->data.p, p->rank.p, (long long)p->n, (int)p->dim, q_dev, (long long)nq, S,
@@ -135,6 +158,7 @@ int b200nn_flat_add(b200nn_flat_t p, const void* vectors, const uint64_t* labels
     }
     p->n += n;
     p->ranks_valid = false;
+    p->tc_rows = -1;
     return 0;
 }
 
@@ -156,6 +180,7 @@ int b200nn_flat_remove(b200nn_flat_t p, uint64_t label) {
     p->labels.pop_back();
     p->n--;
     p->ranks_valid = false;
+    p->tc_rows = -1;
     return 0;
 }
 

@@ -1,0 +1,328 @@
+// u8_scan_tc.cu -- cfg2: exact L2 scan over uint8 vectors as a dense contraction on the tensor cores.
+//
+//   dist(q,x) = sum (q_i - x_i)^2 = |q|^2 + |x|^2 - 2 <q,x>        (L2SqrI, hnswlib/space_l2.h:186-219)
+// <q,x> over uint8 is exact in int32 (128 * 255^2 = 8.3e6), so the scan is a u8 x u8 -> s32 GEMM:
+// tcgen05.mma kind::i8, M = 128 queries, N = 256 database rows, K = D, accumulators in TMEM
+// (2 x 256 columns, double buffered), followed by a fused epilogue that never writes distances:
+// tcgen05.ld brings 32 lanes x 32 columns to registers, d' = |x|^2 - 2 acc is compared with the
+// query's threshold, and the rare survivors go through the exact (dist, label) top-k lists.
+//
+// Roles (160 threads): warps 0-3 = epilogue (thread t owns query t = TMEM lane t, so a query's list is
+// touched by one warp only: no locks); warp 4, one elected thread = TMA producer + MMA issuer.
+//   B tiles (256 rows x D bytes) are stored in HBM already in the K-major no-swizzle core-matrix
+//   order (u8_rows_to_canonical_kernel), so a tile is ONE contiguous TMA bulk copy; |x|^2 rides along.
+// Supported: D % 32 == 0, D <= 256, k <= 32 (otherwise the dp4a kernel of flat_kernels.cu is used).
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "topk.cuh"
+#include "u8_scan_tc.cuh"
+
+namespace b200nn {
+
+constexpr int TC_M = 128;      // queries per CTA (TMEM lanes)
+constexpr int TC_N = 256;      // database rows per tile
+constexpr int TC_KP = 32;      // list slots per query (k <= 32)
+constexpr int TC_SB = 8;       // staged records per query
+constexpr int TC_THREADS = 160;
+
+__device__ __forceinline__ uint64_t tc_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// rank-merge of nb (<= TC_SB) candidates into a sorted list of 32 keys (one per lane); warp-private list
+__device__ __forceinline__ void warp_list_merge32(uint32_t L_addr, uint32_t cand_addr, int nb) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long l = lds64(L_addr + (uint32_t)lane * 8u);
+    const unsigned long long c = lane < nb ? lds64(cand_addr + (uint32_t)lane * 8u) : KEY_MAX;
+    int pl = 0, pc = 0;
+    for (int j = 0; j < nb; j++) {
+        const unsigned long long cj = lds64(cand_addr + (uint32_t)j * 8u);
+        pl += (cj < l) ? 1 : 0;
+        pc += (cj < c) ? 1 : 0;
+    }
+    int pos = 0;
+#pragma unroll
+    for (int step = TC_KP / 2; step >= 1; step >>= 1)
+        if (lds64(L_addr + (uint32_t)(pos + step - 1) * 8u) < c) pos += step;
+    if (lds64(L_addr + (uint32_t)pos * 8u) < c) pos += 1;
+    pc += pos;
+    __syncwarp();
+    if (lane + pl < TC_KP) sts64(L_addr + (uint32_t)(lane + pl) * 8u, l);
+    if (lane < nb && pc < TC_KP) sts64(L_addr + (uint32_t)pc * 8u, c);
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32][8][16] canonical B tiles
+                  const int* __restrict__ xnorm,             // [tiles*256] |x|^2 (padded rows: large)
+                  const uint32_t* __restrict__ rank,         // [n] label rank of each row
+                  long long n, int D, const unsigned char* __restrict__ queries, long long nq, int n_slices, int k,
+                  unsigned long long* __restrict__ out_keys /*[slice][nq][k]*/) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t A_BYTES = (uint32_t)TC_M * D, B_BYTES = (uint32_t)TC_N * D;
+    const uint32_t sA = s_base;
+    const uint32_t sB = sA + A_BYTES;                  // 2 stages
+    // |x|^2 ring: 4 stages, because a tile's norms are read by its epilogue, which may still run after
+    // the tile's shared-memory B stage has been released (the MMA retires first); stage t&3 is
+    // rewritten for tile t+4, whose load is issued only after the epilogue of tile t has signalled
+    const uint32_t sXN = sB + 2 * B_BYTES;             // 4 stages x 256 ints
+    const uint32_t sList = sXN + 4 * TC_N * 4;         // [128][32] keys
+    const uint32_t sStage = sList + TC_M * TC_KP * 8;  // [128][TC_SB] keys
+    const uint32_t sScratch = sStage + TC_M * TC_SB * 8;  // [4 warps][32 columns][32 lanes] words
+    const uint32_t bars = sScratch + 4 * 32 * 32 * 4;
+    const uint32_t b_full = bars, b_empty = bars + 16, acc_full = bars + 32, acc_empty = bars + 48, tmem_slot = bars + 64;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long q0 = (long long)blockIdx.x * TC_M;
+    const int slice = blockIdx.y;
+    const long long n_tiles = (n + TC_N - 1) / TC_N;
+    const long long t_lo = (n_tiles * slice) / n_slices, t_hi = (n_tiles * (slice + 1)) / n_slices;
+    const int T = (int)(t_hi - t_lo);
+    const uint32_t A_LBO = (TC_M / 8) * 128, B_LBO = (TC_N / 8) * 128, SBO = 128;
+    const int ksteps = D / 32;
+
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (lane == 0) {
+            for (int i = 0; i < 2; i++) {
+                mbar_init(b_full + 8 * i, 1);
+                mbar_init(b_empty + 8 * i, 1);
+                mbar_init(acc_full + 8 * i, 1);
+                mbar_init(acc_empty + 8 * i, 4);  // one arrival per epilogue warp
+            }
+            mbar_fence_init();
+        }
+    }
+    // ---- queries -> canonical A tile, |q|^2, lists ----
+    int qn = 0;
+    if (tid < TC_M) {
+        const long long qi = q0 + tid;
+        const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+        for (int c = 0; c < D / 16; c++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (qi < nq) v = __ldg(reinterpret_cast<const uint4*>(queries + qi * D) + c);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) qn = (int)__dp4a(w[e], w[e], (unsigned)qn);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sA + (uint32_t)c * A_LBO + row_off), "r"(v.x), "r"(v.y), "r"(v.z),
+                         "r"(v.w)
+                         : "memory");
+        }
+        for (int j = 0; j < TC_KP; j++) sts64(sList + (uint32_t)(tid * TC_KP + j) * 8u, KEY_MAX);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 4) {
+        // ===== TMA producer + MMA issuer (one thread) =====
+        if (lane == 0 && T > 0) {
+            // D = S32 (2<<4), A = B = unsigned 8-bit (0), K-major, N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+            auto load_tile = [&](int t) {
+                const int s = t & 1;
+                mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES + TC_N * 4);
+                tma_load_1d(sB + (uint32_t)s * B_BYTES, xcan + (size_t)(t_lo + t) * B_BYTES, B_BYTES, b_full + 8 * s);
+                tma_load_1d(sXN + (uint32_t)(t & 3) * TC_N * 4, xnorm + (size_t)(t_lo + t) * TC_N, TC_N * 4, b_full + 8 * s);
+            };
+            load_tile(0);
+            for (int t = 0; t < T; t++) {
+                const int s = t & 1, use = t >> 1;
+                if (t + 1 < T) {
+                    if (t + 1 >= 2) mbar_wait(b_empty + 8 * ((t + 1) & 1), (uint32_t)(((t + 1) >> 1) - 1) & 1u);  // MMAs of tile t-1 done
+                    load_tile(t + 1);
+                }
+                mbar_wait(b_full + 8 * s, (uint32_t)use & 1u);
+                if (t >= 2) mbar_wait(acc_empty + 8 * s, (uint32_t)(use - 1) & 1u);  // epilogue drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + (uint32_t)s * TC_N;
+                for (int ks = 0; ks < ksteps; ks++) {
+                    const uint64_t da = tc_desc_kmajor(sA + (uint32_t)ks * 2 * A_LBO, A_LBO, SBO);
+                    const uint64_t db = tc_desc_kmajor(sB + (uint32_t)s * B_BYTES + (uint32_t)ks * 2 * B_LBO, B_LBO, SBO);
+                    umma_i8(acc, da, db, idesc, ks != 0);
+                }
+                tc_commit(b_empty + 8 * s);   // smem stage reusable once these MMAs retire
+                tc_commit(acc_full + 8 * s);  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: thread t owns query t (TMEM lane t) =====
+        const bool qvalid = q0 + tid < nq;
+        const uint32_t myList = sList + (uint32_t)tid * TC_KP * 8u, myStage = sStage + (uint32_t)tid * TC_SB * 8u;
+        const uint32_t warpList = sList + (uint32_t)(warp * 32) * TC_KP * 8u, warpStage = sStage + (uint32_t)(warp * 32) * TC_SB * 8u;
+        const uint32_t scratch = sScratch + (uint32_t)warp * (32 * 32 * 4);
+        int cnt = 0;
+        // tp = threshold on d' = |x|^2 - 2<q,x>  (dist - |q|^2); INT_MAX while the list is not full
+        int tp = 0x7fffffff;
+        unsigned long long tkey = KEY_MAX;
+        auto flush = [&](unsigned need) {
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const int nb = __shfl_sync(0xffffffffu, cnt, src);
+                warp_list_merge32(warpList + (uint32_t)src * TC_KP * 8u, warpStage + (uint32_t)src * TC_SB * 8u, nb);
+                if (lane == src) {
+                    cnt = 0;
+                    tkey = lds64(myList + (uint32_t)(k - 1) * 8u);
+                    tp = (tkey == KEY_MAX) ? 0x7fffffff : (s32_from_orderable((uint32_t)(tkey >> 32)) - qn);
+                }
+            }
+        };
+        for (int t = 0; t < T; t++) {
+            const int s = t & 1, use = t >> 1;
+            mbar_wait(acc_full + 8 * s, (uint32_t)use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long row_base = (t_lo + t) * TC_N;
+            const uint32_t xn_s = sXN + (uint32_t)(t & 3) * TC_N * 4;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TC_N; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * TC_N + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+                      "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+                      "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t pm = 0;  // bit i: column c0+i passes this lane's threshold
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const uint4 xv = lds128(xn_s + (uint32_t)(c0 + i) * 4u);  // broadcast: |x|^2 of 4 columns
+                    r[i] = (uint32_t)((int)xv.x - 2 * (int)r[i]);
+                    r[i + 1] = (uint32_t)((int)xv.y - 2 * (int)r[i + 1]);
+                    r[i + 2] = (uint32_t)((int)xv.z - 2 * (int)r[i + 2]);
+                    r[i + 3] = (uint32_t)((int)xv.w - 2 * (int)r[i + 3]);
+                    if ((int)r[i] <= tp) pm |= 1u << i;
+                    if ((int)r[i + 1] <= tp) pm |= 2u << i;
+                    if ((int)r[i + 2] <= tp) pm |= 4u << i;
+                    if ((int)r[i + 3] <= tp) pm |= 8u << i;
+                }
+                if (!qvalid) pm = 0;
+                if (__any_sync(0xffffffffu, pm != 0)) {
+                    // park the chunk in the warp's scratch (word i*32+lane: conflict-free) so that the few
+                    // passing columns can be fetched by dynamic index
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch + (uint32_t)(i * 32 + lane) * 4u), "r"(r[i]) : "memory");
+                    while (__any_sync(0xffffffffu, pm != 0)) {
+                        if (pm != 0 && cnt < TC_SB) {
+                            const int i = __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            int dp;
+                            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(dp) : "r"(scratch + (uint32_t)(i * 32 + lane) * 4u));
+                            const long long row = row_base + c0 + i;
+                            if (dp <= tp && row < n) {  // tp may have tightened since the mask was built
+                                const unsigned long long key = make_key(s32_orderable(dp + qn), __ldg(rank + row));
+                                if (key < tkey) {
+                                    sts64(myStage + (uint32_t)cnt * 8u, key);
+                                    cnt++;
+                                }
+                            }
+                        }
+                        const unsigned full = __ballot_sync(0xffffffffu, cnt == TC_SB);
+                        if (full) flush(full);
+                    }
+                    const unsigned soft = __ballot_sync(0xffffffffu, cnt >= TC_SB / 2);
+                    if (soft) flush(soft);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * s);
+        }
+        flush(__ballot_sync(0xffffffffu, cnt > 0));
+        if (qvalid)
+            for (int j = 0; j < k; j++) out_keys[((long long)slice * nq + q0 + tid) * k + j] = lds64(myList + (uint32_t)j * 8u);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// row-major u8 rows -> canonical B tiles + |x|^2
+__global__ void u8_rows_to_canonical_kernel(const unsigned char* __restrict__ rows, long long n, int D, unsigned char* __restrict__ xcan,
+                                            int* __restrict__ xnorm, long long n_pad) {
+    // one thread per (row, 16-byte chunk)
+    const int chunks = D / 16;
+    const long long total = n_pad * chunks;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / chunks;
+        const int c = (int)(i - row * chunks);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < n) v = *reinterpret_cast<const uint4*>(rows + row * D + c * 16);
+        const long long tile = row / TC_N;
+        const int rl = (int)(row - tile * TC_N);
+        unsigned char* dst = xcan + (size_t)tile * TC_N * D + (size_t)c * (TC_N / 8) * 128 + (size_t)(rl >> 3) * 128 + (rl & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = v;
+    }
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n_pad; row += (long long)gridDim.x * blockDim.x) {
+        int s = 0x3fffffff;  // padded rows can never beat a real one
+        if (row < n) {
+            s = 0;
+            for (int j = 0; j < D; j++) {
+                const int v = rows[row * D + j];
+                s += v * v;
+            }
+        }
+        xnorm[row] = s;
+    }
+}
+
+bool u8_scan_tc_supported(int D, int k) { return D % 32 == 0 && D >= 32 && D <= 256 && k >= 1 && k <= TC_KP; }
+
+int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, long long n, int D, unsigned char* xcan, int* xnorm, long long n_pad) {
+    if (n_pad <= 0) return 0;
+    const long long work = n_pad * (D / 16);
+    u8_rows_to_canonical_kernel<<<(unsigned)std::max<long long>(1, std::min<long long>((work + 255) / 256, (long long)ctx->sm_count * 16)), 256,
+                                  0, ctx->stream>>>(rows, n, D, xcan, xnorm, n_pad);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int u8_scan_tc_slices(int sm_count, long long nq, long long n) {
+    const long long qt = (nq + TC_M - 1) / TC_M, tiles = (n + TC_N - 1) / TC_N;
+    long long s = sm_count / qt;  // one wave of one-CTA-per-SM
+    s = std::max<long long>(1, std::min<long long>(s, std::max<long long>(1, tiles / 4)));
+    return (int)std::min<long long>(s, 1024);
+}
+
+int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xnorm, const uint32_t* rank, long long n, int D,
+                      const unsigned char* queries, long long nq, int n_slices, int k, unsigned long long* out_keys) {
+    if (nq <= 0) return 0;
+    if (!u8_scan_tc_supported(D, k)) B2_FAIL(-4, "u8 tensor-core scan: needs D % 32 == 0, D <= 256, k <= 32");
+    const size_t smem = (size_t)TC_M * D + 2 * (size_t)TC_N * D + 4 * TC_N * 4 + (size_t)TC_M * TC_KP * 8 + (size_t)TC_M * TC_SB * 8 + 4 * 32 * 32 * 4 + 128;
+    B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((nq + TC_M - 1) / TC_M), (unsigned)n_slices);
+    u8_scan_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(xcan, xnorm, rank, n, D, queries, nq, n_slices, k, out_keys);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200nn

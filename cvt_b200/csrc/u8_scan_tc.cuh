@@ -1,0 +1,15 @@
+// u8_scan_tc.cuh -- tcgen05 kind::i8 exact L2 scan over uint8 rows (definitions in u8_scan_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200nn {
+
+bool u8_scan_tc_supported(int D, int k);
+// rows [n][D] u8 -> canonical 256-row tiles + |x|^2 (both padded to n_pad = multiple of 256)
+int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, long long n, int D, unsigned char* xcan, int* xnorm, long long n_pad);
+int u8_scan_tc_slices(int sm_count, long long nq, long long n);
+// out_keys [n_slices][nq][k]; ids in the keys are label ranks
+int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xnorm, const uint32_t* rank, long long n, int D,
+                      const unsigned char* queries, long long nq, int n_slices, int k, unsigned long long* out_keys);
+
+}  // namespace b200nn

@@ -172,3 +172,31 @@ def test_sq_roundtrip_property_at_size(ctx):
     od, ol = orc.flat_search(2, 0, codes, np.arange(len(codes), dtype=np.uint64), codes[:2], 10)
     assert np.array_equal(L[:2], ol) and np.array_equal(D[:2], od)
     sq.close(); idx.close()
+
+
+@pytest.mark.parametrize("D,n,nq,k,hi", [(128, 33_333, 130, 10, 256), (32, 1000, 5, 1, 256), (64, 5000, 300, 32, 3), (256, 2049, 129, 7, 256),
+                                          (128, 200, 17, 32, 2)])
+def test_u8_tensor_core_scan_vs_oracle_and_dp4a(ctx, D, n, nq, k, hi):
+    """cfg2 path: tcgen05 kind::i8 GEMM + fused top-k == oracle (L2SqrI + (dist,label) heap rule) == dp4a kernel,
+    on ragged sizes and tie-heavy data (hi=2,3: tiny alphabets -> masses of equal distances)."""
+    from cvt_b200 import capi
+    rng = np.random.Generator(np.random.PCG64(D * 7 + n))
+    xu = rng.integers(0, hi, size=(n, D)).astype(np.uint8)
+    qu = rng.integers(0, hi, size=(nq, D)).astype(np.uint8)
+    labels = (rng.permutation(n).astype(np.uint64) * np.uint64(3)) + np.uint64(11)
+    idx = capi.FlatIndex(ctx, "l2_u8", D, n)
+    idx.add(xu[: n // 2], labels[: n // 2])
+    idx.add(xu[n // 2:], labels[n // 2:])
+    os.environ.pop("B200NN_NO_TC_U8", None)
+    Dt, Lt = idx.search(qu, k)
+    os.environ["B200NN_NO_TC_U8"] = "1"
+    try:
+        Dd, Ld = idx.search(qu, k)
+    finally:
+        os.environ.pop("B200NN_NO_TC_U8", None)
+    assert np.array_equal(Lt, Ld) and np.array_equal(Dt, Dd)
+    sel = range(nq) if n <= 5000 else range(0, nq, 9)
+    for i in sel:
+        od, ol = orc.flat_search(2, 0, xu, labels, qu[i:i + 1], k)
+        assert np.array_equal(Lt[i], ol[0]) and np.array_equal(Dt[i], od[0]), (D, n, i)
+    idx.close()
