@@ -37,6 +37,7 @@ WORKLOADS = {
     # name: n_rows, D, M, batch, k
     "cfg3": dict(n=1_000_000, D=128, M=16, B=4096, k=100, desc="cfg3: OPQ M=16 8-bit, 1M x 128 SIFT-shaped, flat ADC top-100, batch 4096"),
     "cfg3_small": dict(n=100_000, D=128, M=16, B=512, k=100, desc="cfg3 shape at 1/10 size (development)"),
+    "cfg2": dict(n=1_000_000, D=128, M=0, B=1024, k=10, desc="cfg2: int8 scalar-quantized exact L2 scan, 1M x 128 SIFT-shaped, batch 1024, top-10"),
     "cfg4_shard": dict(n=1_250_000, D=512, M=32, B=4096, k=100, desc="cfg4 per-GPU shard: OPQ M=32, 1.25M x 512 CNN-like, ADC top-100, batch 4096"),
 }
 METRIC = "queries/sec, batched ADC top-k scan (HBM GB/s in roofline; recall@10 vs CPU reference)"
@@ -145,6 +146,85 @@ def run_reference_sample(wl, inputs, n_queries, repeat, threads=0):
     return r
 
 
+def run_cfg2(args, wl, local_rank):
+    """Secondary workload (BASELINE.json configs[1]): exact L2 scan over 8-bit scalar-quantized codes.
+    SQ encode on the GPU (Int8Quan arithmetic), then the tcgen05 kind::i8 scan with fused top-k."""
+    import torch
+    from cvt_b200 import capi
+    n, D, B, k = wl["n"], wl["D"], wl["B"], wl["k"]
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = capi.Context(local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    x = synth.sift_like(n, D, seed=synth.SEED_DB)
+    vmin, vdiff = capi.SQ.train_minmax(ctx, x[:200_000])
+    sq = capi.SQ(ctx, vmin, vdiff)
+    codes, _ = sq.encode(x, l2norm=True)
+    qc, _ = sq.encode(synth.sift_like(B, D, seed=synth.SEED_QUERY), l2norm=True)
+    labels = np.arange(n, dtype=np.uint64)
+    idx = capi.FlatIndex(ctx, "l2_u8", D, n)
+    idx.add(codes, labels)
+    q_pinned = torch.from_numpy(qc).pin_memory()
+    q_dev = q_pinned.cuda()
+    od = torch.empty((B, k), dtype=torch.int32, device="cuda")
+    ol = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(args.warmup):
+        idx.search_dev(q_dev.data_ptr(), B, k, od.data_ptr(), ol.data_ptr())
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        idx.search_dev(q_dev.data_ptr(), B, k, od.data_ptr(), ol.data_ptr())
+        b.record()
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    ms_per_step = float(np.mean(ms))
+    res_l, res_d = ol.cpu().numpy(), od.cpu().numpy()
+    Dh = np.empty((B, k), dtype=np.int32)
+    Lh = np.empty((B, k), dtype=np.uint64)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Dh, Lh = idx.search(qc, k)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    assert np.array_equal(Lh.astype(np.int64), res_l) and np.array_equal(Dh, res_d)
+    ops = 2.0 * B * n * D
+    peak = None
+    try:
+        peak = 2.0 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        peak = 2.0 * 1590.0
+    line = {"metric": "queries/sec, batched exact int8 L2 top-10 scan", "value": B / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8 x u8 -> s32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "n_rows": n, "dim": D, "batch": B, "k": k, "l2": "256 MB buffer written between timed iterations"},
+            "roofline": {"bound": "tensor", "kernel": "u8_scan_tc_kernel (+merge)", "achieved": ops / (ms_per_step * 1e-3) / 1e12, "peak": peak,
+                         "unit": "TOP/s", "frac": ops / (ms_per_step * 1e-3) / 1e12 / peak, "traffic": None,
+                         "peak_source": "2 x measured bf16 cuBLAS TF/s (MEASURED_PEAKS.json): dense int8 is nominally twice bf16"},
+            "e2e": {"value": B / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(B * D), "d2h_bytes_per_step": int(B * k * 12)},
+            "gpu_launches": int(launches), "clocks": clocks}
+    if not args.no_cpu_baseline:
+        from oracle import oracle as orc  # checker / CPU baseline only
+        ns = 4
+        t0 = time.perf_counter()
+        odist, olab = orc.flat_search(2, 0, codes, labels, qc[:ns], k)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+                                "sample": f"first {ns} queries, oracle restatement of BruteforceSearch<int> + L2SqrI (scalar, 1 thread)"}
+        line["parity"] = {"queries_checked": ns, "labels_identical": bool(np.array_equal(olab.astype(np.int64), res_l[:ns])),
+                          "dists_identical": bool(np.array_equal(odist, res_d[:ns]))}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +244,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        if args.workload == "cfg2":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is wired for the ADC workloads; cfg2's CPU baseline is in its own line"}))
+            return 0
         inputs = make_inputs(wl)
         ns = min(B, args.cpu_sample)
         r = run_reference_sample(wl, inputs, ns, repeat=args.steps + args.warmup)
@@ -181,6 +264,10 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm (CUDA)
+    if args.workload == "cfg2":
+        if rank != 0:
+            return 0
+        return run_cfg2(args, wl, local_rank)
     import torch
     import torch.distributed as dist
     from cvt_b200 import capi, sharded

@@ -1,0 +1,144 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle cannot scan
+4096 x 1M pairs in a test): sortedness, exact recomputation of returned scores, an exact oracle scan
+for a few queries, top-10 = prefix of top-100, shard -> all-gather-layout -> merge == single index
+(the multi-GPU exchange run on one device), tensor-core u8 scan == dp4a scan."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cvt_b200 import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from cvt_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def cfg3():
+    n, D, M, B = 1_000_000, 128, 16, 4096
+    db = synth.sift_like(n, D, seed=synth.SEED_DB)
+    q = synth.sift_like(B, D, seed=synth.SEED_QUERY)
+    perm = synth.SHIPPED_REORDER_128
+    coarse, cb = synth.train_pq_model(db[:20000][:, perm], M, 256, 1, iters=4, seed=synth.SEED_KMEANS, train_rows=20000)
+    return dict(n=n, D=D, M=M, B=B, db=db, q=q, perm=perm, coarse=coarse, cb=cb)
+
+
+def _search_dev(ctx, idx, q_t, k, id_base=0):
+    nq = q_t.shape[0]
+    d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    keys = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    idx.search_dev(q_t.data_ptr(), nq, k, 1, d.data_ptr(), i.data_ptr(), keys.data_ptr(), id_base)
+    ctx.synchronize()
+    return d, i, keys
+
+
+def test_cfg3_full_size_properties(ctx, cfg3):
+    from cvt_b200 import capi
+    c = cfg3
+    idx = capi.PQIndex.create(ctx, c["coarse"], c["cb"], perm=c["perm"], clamp=1.0)
+    idx.add(c["db"])
+    q_t = torch.from_numpy(c["q"]).cuda()
+    d100, i100, k100 = _search_dev(ctx, idx, q_t, 100)
+    D100, I100 = d100.cpu().numpy(), i100.cpu().numpy()
+    # sorted by (dist, id), ids unique and in range
+    assert np.all(np.diff(D100, axis=1) >= 0)
+    tie = np.diff(D100, axis=1) == 0
+    assert np.all(np.diff(I100, axis=1)[tie] > 0)
+    assert I100.min() >= 0 and I100.max() < c["n"]
+    assert all(len(set(r)) == 100 for r in I100[::97])
+    # the sanity gate of SURVEY.md 8(d): the k-th best is below the clamp for > 99 % of the queries
+    assert (D100[:, -1] < 1.0).mean() > 0.99
+    # top-10 is the prefix of top-100
+    d10, i10, _ = _search_dev(ctx, idx, q_t, 10)
+    assert torch.equal(i10, i100[:, :10]) and torch.equal(d10, d100[:, :10])
+    # idempotent
+    d_again, i_again, _ = _search_dev(ctx, idx, q_t, 100)
+    assert torch.equal(i_again, i100) and torch.equal(d_again, d100)
+    # returned scores are exactly the reference's sequential LUT sums; exact oracle scan for a few queries
+    _, _, codes = idx.get_rows()
+    qr = orc.opq_reorder(c["q"], c["perm"])
+    for qi in (0, 1, 2047, 4095):
+        lut = orc.opq_build_lut(qr[qi], c["coarse"][0], c["cb"])
+        s = np.minimum(orc.opq_adc_scan(lut, codes), np.float32(1.0))
+        os_, oi = orc.topk_pairs(s, 100)
+        assert np.array_equal(I100[qi], oi) and np.array_equal(D100[qi].view(np.uint32), os_.view(np.uint32))
+    for qi in range(5, 4096, 409):
+        lut = orc.opq_build_lut(qr[qi], c["coarse"][0], c["cb"])
+        s = np.minimum(orc.opq_adc_scan(lut, codes[I100[qi]]), np.float32(1.0))
+        assert np.array_equal(s.view(np.uint32), D100[qi].view(np.uint32))
+    # row shards + key exchange layout + merge kernel == single index (the 8-GPU path on one device)
+    G = 8
+    from cvt_b200 import sharded
+    gathered = torch.empty((G, c["B"], 100), dtype=torch.int64, device="cuda")
+    for r in range(G):
+        lo, hi = sharded.shard_bounds(c["n"], G, r)
+        sh = capi.PQIndex.create(ctx, c["coarse"], c["cb"], perm=c["perm"], clamp=1.0)
+        sh.add(c["db"][lo:hi])
+        _, _, keys = _search_dev(ctx, sh, q_t, 100, id_base=lo)
+        gathered[r] = keys
+        sh.close()
+    dm = torch.empty((c["B"], 100), dtype=torch.float32, device="cuda")
+    im = torch.empty((c["B"], 100), dtype=torch.int64, device="cuda")
+    ctx.topk_merge_dev(gathered.data_ptr(), G, c["B"], 100, dm.data_ptr(), im.data_ptr())
+    ctx.synchronize()
+    assert torch.equal(im, i100) and torch.equal(dm, d100)
+    idx.close()
+
+
+def test_cfg2_full_size_u8_scan(ctx):
+    """int8 scalar-quantized L2 scan, 1M x 128, batch 1024: SQ codes from the GPU encoder, tensor-core scan."""
+    from cvt_b200 import capi
+    n, D, B, k = 1_000_000, 128, 1024, 10
+    x = synth.sift_like(n, D, seed=synth.SEED_DB)
+    vmin, vdiff = capi.SQ.train_minmax(ctx, x[:200_000])
+    sq = capi.SQ(ctx, vmin, vdiff)
+    codes, _ = sq.encode(x, l2norm=True)
+    oc, _ = orc.sq_encode(x[::50_000], vmin, vdiff, True)
+    assert np.array_equal(codes[::50_000], oc)
+    qc, _ = sq.encode(synth.sift_like(B, D, seed=synth.SEED_QUERY), l2norm=True)
+    labels = np.arange(n, dtype=np.uint64)
+    idx = capi.FlatIndex(ctx, "l2_u8", D, n)
+    idx.add(codes, labels)
+    Dt, Lt = idx.search(qc, k)
+    assert np.all(np.diff(Dt.astype(np.int64), axis=1) >= 0)
+    os.environ["B200NN_NO_TC_U8"] = "1"
+    try:
+        Dd, Ld = idx.search(qc[:64], k)  # dp4a kernel
+    finally:
+        os.environ.pop("B200NN_NO_TC_U8", None)
+    assert np.array_equal(Lt[:64], Ld) and np.array_equal(Dt[:64], Dd)
+    od, ol = orc.flat_search(2, 0, codes, labels, qc[:3], k)
+    assert np.array_equal(Lt[:3], ol) and np.array_equal(Dt[:3], od)
+    sq.close(); idx.close()
+
+
+def test_cfg4_shape_m32_d512(ctx):
+    """cfg4's shape (OPQ M=32 over 512-d CNN-like features) on a 200k-row shard, batch 512, top-100."""
+    from cvt_b200 import capi
+    n, D, M, B, k = 200_000, 512, 32, 512, 100
+    db = synth.cnn_like(n, D, seed=synth.SEED_DB)
+    q = synth.cnn_like(B, D, seed=synth.SEED_QUERY)
+    perm = synth.random_permutation(D)
+    coarse, cb = synth.train_pq_model(db[:8000][:, perm], M, 256, 1, iters=2, seed=synth.SEED_KMEANS, train_rows=8000)
+    idx = capi.PQIndex.create(ctx, coarse, cb, perm=perm, clamp=np.inf)
+    idx.add(db)
+    Dg, Ig = idx.search(q, k)
+    _, _, codes = idx.get_rows()
+    xr = orc.opq_reorder(db[:2000], perm)
+    assert np.array_equal(codes[:2000], orc.opq_pq_encode(xr, coarse, np.zeros(2000, np.int32), cb))
+    qr = orc.opq_reorder(q, perm)
+    for qi in (0, 255, 511):
+        s = orc.opq_adc_scan(orc.opq_build_lut(qr[qi], coarse[0], cb), codes)
+        os_, oi = orc.topk_pairs(s, k)
+        assert np.array_equal(Ig[qi].astype(np.int64), oi) and np.array_equal(Dg[qi].view(np.uint32), os_.view(np.uint32))
+    idx.close()
