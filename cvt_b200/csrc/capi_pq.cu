@@ -287,25 +287,15 @@ int search_dev_locked(b200nn_pq* p, const float* q_raw_dev, long long nq, int np
         if ((rc = launch_topk_merge(c, p->ws_keys.p, S, nq, k, qgroups * QW * k, out_dist, nullptr, out_id, out_key))) return rc;
         B2_CUDA(cudaEventRecord(ev[4], c->stream));
     } else {
-        // generic path: probe lists, per-row scores in a dense clamp-initialised row (videoId = row),
-        // then get_sort_results.  Query chunks bound the dense buffer.
+        // IVF path (any K): coarse probes, then one fused CTA per query: residual LUT + list scan + top-k
         if ((rc = ensure_csr(p))) return rc;
-        const long long n = std::max<long long>(p->n, 1);
-        const long long qc = std::max<long long>(1, std::min<long long>(nq, (1LL << 28) / n));
-        if ((rc = p->ws_probes.ensure((size_t)qc * nprobe)) || (rc = p->ws_lut.ensure((size_t)qc * nprobe * p->M * p->ksub)) ||
-            (rc = p->ws_scores.ensure((size_t)qc * n)) || (rc = p->ws_keys.ensure((size_t)nq * k)))
-            return rc;
+        if ((rc = p->ws_probes.ensure((size_t)nq * nprobe)) || (rc = p->ws_keys.ensure((size_t)nq * k))) return rc;
+        if (p->K == 1) B2_CUDA(cudaMemsetAsync(p->ws_probes.p, 0, sizeof(int) * nq * nprobe, c->stream));
+        else if ((rc = launch_coarse_probe(c, qr, nq, p->D, p->coarseT.p, p->K, nprobe, p->ws_probes.p))) return rc;
         B2_CUDA(cudaEventRecord(ev[2], c->stream));
-        for (long long q0 = 0; q0 < nq; q0 += qc) {
-            const long long cq = std::min(qc, nq - q0);
-            if ((rc = probes_and_luts(p, qr + q0 * p->D, cq, nprobe, p->ws_probes.p, p->ws_lut.p))) return rc;
-            if ((rc = launch_fill_f32(c, p->ws_scores.p, cq * n, p->clamp))) return rc;
-            if ((rc = launch_ivf_scan(c, p->ws_lut.p, p->ws_probes.p, p->list_off.p, p->codes_sorted.p, p->row_sorted.p, p->M,
-                                      p->ksub, cq, nprobe, n, p->ws_scores.p)))
-                return rc;
-            if ((rc = launch_dense_select_topk(c, p->ws_scores.p, cq, p->n, n, k, (uint32_t)id_base, p->ws_keys.p + q0 * k)))
-                return rc;
-        }
+        if ((rc = launch_ivf_search_topk(c, qr, nq, p->D, p->ws_probes.p, nprobe, p->coarse.p, p->cb.p, p->M, p->ksub, p->list_off.p,
+                                         p->codes_sorted.p, p->row_sorted.p, p->n, k, p->clamp, (uint32_t)id_base, p->ws_keys.p)))
+            return rc;
         B2_CUDA(cudaEventRecord(ev[3], c->stream));
         if ((rc = launch_topk_merge(c, p->ws_keys.p, 1, nq, k, nq * k, out_dist, nullptr, out_id, out_key))) return rc;
         B2_CUDA(cudaEventRecord(ev[4], c->stream));

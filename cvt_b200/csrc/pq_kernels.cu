@@ -574,6 +574,102 @@ __global__ void ivf_scan_kernel(const float* __restrict__ lut,            // [nq
     }
 }
 
+// =============================================================================================
+// f-1: true IVF search with per-row ids (videoId = row), fused: one CTA per query walks its nprobe
+// lists; for each it builds the residual LUT in shared memory (IVFOPQ.cpp:376-398), scans the list
+// (IVFOPQ.cpp:403-411) and feeds the exact top-k lists -- no dense [queries x rows] score matrix.
+// Reference semantics kept: every row starts at `clamp` (matchScore initialised to threhold,
+// IVFOPQ.cpp:369) and get_sort_results breaks ties by id, so when fewer than k probed rows score
+// below the clamp the tail is the smallest row ids at exactly `clamp` (probed or not).
+// =============================================================================================
+template <int DS>
+__global__ void __launch_bounds__(256)
+ivf_search_topk_kernel(const float* __restrict__ q_rot, long long nq, int D, const int* __restrict__ probes, int nprobe,
+                       const float* __restrict__ coarse, const float* __restrict__ cb, int M, int ksub,
+                       const long long* __restrict__ list_off, const unsigned char* __restrict__ codes_sorted,
+                       const int* __restrict__ row_sorted, long long n_rows, int k, float clamp, uint32_t id_base,
+                       unsigned long long* __restrict__ out_keys) {
+    constexpr int SBW = 64;
+    extern __shared__ __align__(16) unsigned char dsm[];
+    float* s_lut = reinterpret_cast<float*>(dsm);                 // [M*ksub]
+    float* s_res = s_lut + M * ksub;                              // [D]
+    __shared__ __align__(16) unsigned long long s_list[KP];
+    __shared__ __align__(16) unsigned long long s_stage[8][SBW];
+    __shared__ unsigned long long s_tau;
+    __shared__ int s_lock;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long q = blockIdx.x;
+    for (int i = threadIdx.x; i < KP; i += blockDim.x) s_list[i] = KEY_MAX;
+    if (threadIdx.x == 0) { s_tau = KEY_MAX; s_lock = 0; }
+    const uint32_t L = smem_u32(s_list), ST = smem_u32(&s_stage[w][0]);
+    volatile unsigned long long* tau_p = &s_tau;
+    int cnt = 0;
+    auto flush_all = [&]() {
+        for (int off = 0; off < cnt; off += 32) warp_flush(L, &s_lock, tau_p, ST + off * 8, min(32, cnt - off), k);
+        cnt = 0;
+    };
+    const uint32_t clamp_ord = f32_orderable(clamp);
+    for (int p = 0; p < nprobe; p++) {
+        const int vw = probes[q * nprobe + p];
+        __syncthreads();  // previous LUT fully consumed; lists initialised
+        for (int j = threadIdx.x; j < D; j += blockDim.x) s_res[j] = __fsub_rn(q_rot[q * D + j], coarse[(long long)vw * D + j]);
+        __syncthreads();
+        for (int e = threadIdx.x; e < M * ksub; e += blockDim.x) {
+            const int m = e / ksub, j = e - m * ksub;
+            const float* c = cb + ((long long)m * ksub + j) * DS;
+            float acc = 0.0f;
+#pragma unroll
+            for (int t = 0; t < DS; t++) {
+                const float d = __fsub_rn(s_res[m * DS + t], __ldg(c + t));
+                acc = __fadd_rn(acc, __fmul_rn(d, d));
+            }
+            s_lut[e] = acc;
+        }
+        __syncthreads();
+        const long long lo = list_off[vw], hi = list_off[vw + 1];
+        for (long long r0 = lo + (long long)w * 32; r0 < hi; r0 += 8 * 32) {
+            const long long r = r0 + lane;
+            bool pass = false;
+            unsigned long long key = 0;
+            if (r < hi) {
+                const unsigned char* c = codes_sorted + r * M;
+                float score = 0.0f;
+                for (int m = 0; m < M; m++) score = __fadd_rn(score, s_lut[m * ksub + c[m]]);
+                if (score < clamp) {  // rows at or above the clamp are indistinguishable from unprobed rows
+                    key = make_key(f32_orderable(score), id_base + (uint32_t)row_sorted[r]);
+                    pass = key < *tau_p;
+                }
+            }
+            const unsigned msk = __ballot_sync(0xffffffffu, pass);
+            if (msk) {
+                if (pass) sts64(ST + (uint32_t)(cnt + __popc(msk & ((1u << lane) - 1))) * 8u, key);
+                cnt += __popc(msk);
+                __syncwarp();
+                if (cnt > SBW - 32) flush_all();
+            }
+        }
+    }
+    flush_all();
+    __syncthreads();
+    if (w == 0) {
+        // how many real records, then fill with (clamp, smallest ids not already present)
+        int real = 0;
+        for (int j = lane; j < k; j += 32) real += (s_list[j] != KEY_MAX) ? 1 : 0;
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) real += __shfl_xor_sync(0xffffffffu, real, sft);
+        if (real < k && lane == 0) {
+            int filled = real;
+            for (long long id = 0; id < n_rows && filled < k; id++) {
+                bool present = false;
+                for (int j = 0; j < real; j++) present |= ((uint32_t)(s_list[j] & 0xFFFFFFFFull) == id_base + (uint32_t)id);
+                if (!present) s_list[filled++] = make_key(clamp_ord, id_base + (uint32_t)id);
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += blockDim.x) out_keys[q * k + j] = s_list[j];
+}
+
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -825,6 +921,31 @@ int launch_ivf_scan(Ctx* ctx, const float* lut, const int* probes, const long lo
     if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(ivf_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ivf_scan_kernel<<<(unsigned)(nq * nprobe), 256, smem, ctx->stream>>>(lut, probes, list_off, codes_sorted, slot_sorted, M,
                                                                          ksub, nprobe, out_stride, out);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_ivf_search_topk(Ctx* ctx, const float* q_rot, long long nq, int D, const int* probes, int nprobe, const float* coarse,
+                           const float* cb, int M, int ksub, const long long* list_off, const unsigned char* codes_sorted,
+                           const int* row_sorted, long long n_rows, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
+    if (nq <= 0) return 0;
+    if (k < 1 || k > KP) B2_FAIL(-4, "IVF search supports 1 <= k <= 128");
+    const int ds = D / M;
+    const size_t smem = ((size_t)M * ksub + D) * sizeof(float);
+#define B2_IVF(DS_)                                                                                                          \
+    case DS_:                                                                                                                \
+        if (smem > 40 * 1024)                                                                                                \
+            B2_CUDA(cudaFuncSetAttribute(ivf_search_topk_kernel<DS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ivf_search_topk_kernel<DS_><<<(unsigned)nq, 256, smem, ctx->stream>>>(q_rot, nq, D, probes, nprobe, coarse, cb, M, ksub, \
+                                                                             list_off, codes_sorted, row_sorted, n_rows, k, clamp, \
+                                                                             id_base, out_keys);                              \
+        break;
+    switch (ds) {
+        B2_IVF(1) B2_IVF(2) B2_IVF(4) B2_IVF(8) B2_IVF(16) B2_IVF(32)
+        default: B2_FAIL(-4, "ivf_search: unsupported sub-vector dimension");
+    }
+#undef B2_IVF
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

@@ -207,3 +207,29 @@ def test_save_load_index_roundtrip(ctx, tmp_path):
     assert idx2.n_rows == c["n"] and idx2.n_groups == idx.n_groups
     assert np.array_equal(_bits(idx2.scores(c["q"], nprobe=3)), _bits(ref_scores))
     idx.close(); idx2.close()
+
+
+@pytest.mark.parametrize("clamp", [1.0, np.inf])
+def test_ivf_fused_search_vs_oracle(ctx, clamp):
+    """f-1: true IVF probing (K=16 lists, nprobe=3) with per-row ids through the fused LUT+scan+top-k
+    kernel == the reference semantics restated by the oracle (dense clamp-initialised scores, then
+    get_sort_results), including the clamp-valued tail that is filled by id order."""
+    from cvt_b200 import capi
+    c = cases.opq_case("ivf_m8")
+    idx = capi.PQIndex.create(ctx, c["coarse"], c["cb"], perm=c["reorder"], clamp=clamp)
+    idx.add(c["db"])  # videoId = row
+    lists, groups, codes = idx.get_rows()
+    assert np.array_equal(groups, np.arange(c["n"], dtype=np.int32))
+    q = np.concatenate([c["q"], c["q"] * np.float32(3.0)])  # the scaled copies push most scores over the clamp
+    k = 50
+    Dg, Ig = idx.search(q, k=k, nprobe=3)
+    qr = orc.opq_reorder(q, c["reorder"])
+    dense = orc.opq_query_scores(qr, c["coarse"], c["cb"], 3, lists, groups, codes, c["n"], clamp)
+    ntail = 0
+    for i in range(len(q)):
+        os_, oi = orc.topk_pairs(dense[i], k)
+        assert np.array_equal(Ig[i].astype(np.int64), oi), i
+        assert np.array_equal(_bits(Dg[i]), _bits(os_)), i
+        ntail += int((os_ == np.float32(clamp)).sum()) if np.isfinite(clamp) else int(np.isinf(os_).sum())
+    assert ntail > 0 or not np.isfinite(clamp)  # the finite clamp case must exercise the id-ordered tail
+    idx.close()
