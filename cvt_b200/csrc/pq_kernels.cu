@@ -476,21 +476,25 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
         // Bg = block counter of lane group 0; this lane's block is Bg - h.  Only lanes of the last
         // lane group can satisfy mn <= tau (tau = -inf elsewhere).
         if (mn <= tau) {
+            // usually exactly one of the 4 rows qualifies: peel minima until none is left under the threshold
             const uint32_t rel0 = (uint32_t)(Bg - h) * 4u;
-            const float sc[4] = {o0, o1, o2, o3};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float s = sc[j];
-                s = clamp < s ? clamp : s;  // std::min(score, threhold-initialised slot), IVFOPQ.cpp:410
-                if (s <= tsc && rel0 + j < nrel) {
+            float a0 = o0, a1 = o1, a2 = o2, a3 = o3, m = mn;
+            do {
+                const int j = (a0 == m) ? 0 : (a1 == m) ? 1 : (a2 == m) ? 2 : 3;
+                const float s = clamp < m ? clamp : m;  // std::min(score, threhold-initialised slot), IVFOPQ.cpp:410
+                const uint32_t rel = rel0 + (uint32_t)j;
+                if (s <= tsc && rel < nrel) {
                     // scores are sums of squares (>= +0): the orderable form is just the sign bit set
-                    const uint32_t ord = __float_as_uint(s) | 0x80000000u, id = idbase + rel0 + j;
+                    const uint32_t ord = __float_as_uint(s) | 0x80000000u, id = idbase + rel;
                     if (s < tsc || make_key(ord, id) < tkey) {
                         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(my_staging + (uint32_t)cnt * 8u), "r"(id), "r"(ord) : "memory");
                         cnt++;
                     }
                 }
-            }
+                const float inf = __int_as_float(0x7f800000);
+                a0 = (j == 0) ? inf : a0; a1 = (j == 1) ? inf : a1; a2 = (j == 2) ? inf : a2; a3 = (j == 3) ? inf : a3;
+                m = fminf(fminf(a0, a1), fminf(a2, a3));
+            } while (m <= tau && m < __int_as_float(0x7f800000));
         }
         const unsigned soft = __ballot_sync(0xffffffffu, cnt >= C::SOFT);
         if (soft) {
@@ -672,50 +676,6 @@ ivf_search_topk_kernel(const float* __restrict__ q_rot, long long nq, int D, con
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
-}
-
-// =============================================================================================
-// Dense select (get_sort_results, opq/src/common.h:25-37): k smallest (score, id) of a dense
-// score row.  One CTA per query, warps stride over the row, ballot-compacted staging.
-// =============================================================================================
-__global__ void dense_select_topk_kernel(const float* __restrict__ scores, long long n, long long stride, int k,
-                                         uint32_t id_base, unsigned long long* __restrict__ out_keys) {
-    constexpr int SBW = 64;
-    __shared__ __align__(16) unsigned long long s_list[KP];
-    __shared__ __align__(16) unsigned long long s_stage[8][SBW];
-    __shared__ unsigned long long s_tau;
-    __shared__ int s_lock;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const long long q = blockIdx.x;
-    for (int i = threadIdx.x; i < KP; i += blockDim.x) s_list[i] = KEY_MAX;
-    if (threadIdx.x == 0) { s_tau = KEY_MAX; s_lock = 0; }
-    __syncthreads();
-    const uint32_t L = smem_u32(s_list), ST = smem_u32(&s_stage[w][0]);
-    volatile unsigned long long* tau_p = &s_tau;
-    int cnt = 0;
-    const float* row = scores + q * stride;
-    auto flush_all = [&]() {
-        for (int off = 0; off < cnt; off += 32)
-            warp_flush(L, &s_lock, tau_p, ST + off * 8, min(32, cnt - off), k);
-        cnt = 0;
-    };
-    for (long long i0 = (long long)w * 32; i0 < n; i0 += (long long)nw * 32) {
-        const long long i = i0 + lane;
-        const unsigned long long tkey = *tau_p;
-        bool pass = false;
-        unsigned long long key = 0;
-        if (i < n) { key = make_key(f32_orderable(row[i]), id_base + (uint32_t)i); pass = key < tkey; }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            if (pass) sts64(ST + (uint32_t)(cnt + __popc(m & ((1u << lane) - 1))) * 8u, key);
-            cnt += __popc(m);
-            __syncwarp();
-            if (cnt > SBW - 32) flush_all();
-        }
-    }
-    flush_all();
-    __syncthreads();
-    for (int j = threadIdx.x; j < k; j += blockDim.x) out_keys[q * k + j] = s_list[j];
 }
 
 // =============================================================================================
@@ -946,16 +906,6 @@ int launch_ivf_search_topk(Ctx* ctx, const float* q_rot, long long nq, int D, co
         default: B2_FAIL(-4, "ivf_search: unsupported sub-vector dimension");
     }
 #undef B2_IVF
-    ctx->launches++;
-    B2_CUDA(cudaGetLastError());
-    return 0;
-}
-
-int launch_dense_select_topk(Ctx* ctx, const float* scores, long long nq, long long n, long long stride, int k,
-                             uint32_t id_base, unsigned long long* out_keys) {
-    if (nq == 0) return 0;
-    if (k < 1 || k > KP) B2_FAIL(-4, "dense select supports 1 <= k <= 128");
-    dense_select_topk_kernel<<<(unsigned)nq, 256, 0, ctx->stream>>>(scores, n, stride, k, id_base, out_keys);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

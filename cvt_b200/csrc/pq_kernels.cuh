@@ -25,7 +25,5 @@ int launch_ivf_scan(Ctx* ctx, const float* lut, const int* probes, const long lo
 int launch_ivf_search_topk(Ctx* ctx, const float* q_rot, long long nq, int D, const int* probes, int nprobe, const float* coarse,
                            const float* cb, int M, int ksub, const long long* list_off, const unsigned char* codes_sorted,
                            const int* row_sorted, long long n_rows, int k, float clamp, uint32_t id_base, unsigned long long* out_keys);
-int launch_dense_select_topk(Ctx* ctx, const float* scores, long long nq, long long n, long long stride, int k,
-                             uint32_t id_base, unsigned long long* out_keys);
 
 }  // namespace b200nn
