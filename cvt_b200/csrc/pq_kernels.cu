@@ -819,15 +819,6 @@ void scan_plan(int sm_count, long long qgroups, long long n_granules, int* n_ful
     *tail_s = (int)s;
 }
 
-static int scan_warps_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("B200NN_SCAN_WARPS");
-        v = (e && atoi(e) == 24) ? 24 : 16;
-    }
-    return v;
-}
-
 template <int G, int WARPS_>
 static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
                        int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
@@ -849,8 +840,6 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
 template <int G>
 static int scan_dispatch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
                          int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
-    if (G == 4 && scan_warps_variant() == 24)
-        return scan_launch<G, 24>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
     return scan_launch<G, 16>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
 }
 
