@@ -33,7 +33,7 @@ struct b200nn_pq {
     DevBuf<int> group_sorted, row_sorted;
     DevBuf<long long> list_off;
     // workspaces
-    DevBuf<float> ws_x, ws_q, ws_qraw, ws_lut, ws_scores, ws_dist;
+    DevBuf<float> ws_x, ws_q, ws_qraw, ws_lut, ws_scores, ws_dist, ws_warm;
     DevBuf<int> ws_probes, ws_list;
     DevBuf<unsigned char> ws_codes;
     DevBuf<unsigned long long> ws_keys, ws_keys2, ws_id;
@@ -280,8 +280,9 @@ int search_dev_locked(b200nn_pq* p, const float* q_raw_dev, long long nq, int np
         if ((rc = p->ws_keys.ensure((size_t)S * qgroups * QW * k))) return rc;
         if (S > 1)  // whole-shard CTAs write slice 0 only: the other slices of those queries stay empty (KEY_MAX)
             B2_CUDA(cudaMemsetAsync(p->ws_keys.p, 0xFF, (size_t)S * qgroups * QW * k * sizeof(unsigned long long), c->stream));
+        if ((rc = p->ws_warm.ensure(scan_warm_scratch_floats(p->M, qgroups, n_full, tail_s)))) return rc;
         if ((rc = launch_adc_scan_topk(c, p->M, p->codesT.p, p->ws_lut.p, p->n, qgroups, n_full, tail_s, k, p->clamp,
-                                       (uint32_t)id_base, p->ws_keys.p)))
+                                       (uint32_t)id_base, p->ws_keys.p, p->ws_warm.p)))
             return rc;
         B2_CUDA(cudaEventRecord(ev[3], c->stream));
         if ((rc = launch_topk_merge(c, p->ws_keys.p, S, nq, k, qgroups * QW * k, out_dist, nullptr, out_id, out_key))) return rc;

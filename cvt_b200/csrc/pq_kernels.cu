@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "pq_kernels.cuh"
 #include "topk.cuh"
@@ -306,6 +307,13 @@ struct ScanCfg {
     static constexpr int SOFT = SB / 2;
     static constexpr int STAGING_BYTES = QW * SB * 8;          // per warp
     static constexpr int LIST_BYTES = QW * KP * 8;
+    // Warm-up: the first WARM_STAGES stages of every warp are not filtered at all -- their raw scores are
+    // parked in global scratch and the CTA then selects their top-k in one dense pass (lanes over rows),
+    // which is far cheaper per record than the streaming candidate path that a k(1+ln(n/k)) warm-up
+    // would otherwise take for exactly these rows.
+    static constexpr int WARM_STAGES = (G <= 4) ? 2 : 4;
+    static constexpr int WARM_BLOCKS = WARM_STAGES * STAGE_BLOCKS;   // 32 blocks = 128 rows per warp
+    static constexpr int WARM_ROWS = WARM_BLOCKS * 4;
     static constexpr int LUT_BYTES = 131072;
     static constexpr int SMEM_BYTES = 232448;                  // 227 KB: one CTA per SM
 };
@@ -339,6 +347,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                      int n_full, int tail_s, int k, float clamp, uint32_t id_base,
                      unsigned long long* __restrict__ out_keys,  // [slice][qgroups*QW][k]
                      long long q_stride_total,                   // qgroups*QW
+                     float* __restrict__ warm_scratch,           // [grid][QW][WARPS][WARM_ROWS] raw scores of the warm-up rows
                      int* __restrict__ err_flag) {
     using C = ScanCfg<G, WARPS_>;
     constexpr int QW = C::QW;
@@ -374,6 +383,8 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     unsigned char* generic_base = dyn_smem - base;  // generic pointer of shared-window address 0
     volatile unsigned long long* tau_key = (volatile unsigned long long*)(generic_base + misc + 1024);
     int* locks = (int*)(generic_base + misc + 1536);
+    unsigned int* warm_valid = (unsigned int*)(generic_base + misc + 1700);   // [WARPS] parked rows per warp
+    unsigned int* warm_idbase = (unsigned int*)(generic_base + misc + 1800);  // [WARPS] id of a warp's first row
 
     // ---- this warp's stream of rows ----
     const long long g_lo = (n_granules * slice) / n_slices, g_hi = (n_granules * (slice + 1)) / n_slices;
@@ -450,6 +461,8 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     // 32-bit row bookkeeping for the candidate path: valid relative rows are [0, nrel)
     const uint32_t nrel = (uint32_t)max(0LL, min((long long)nblocks * 4, n_rows - row0));
     const uint32_t idbase = id_base + (uint32_t)row0;
+    // number of leading blocks of this warp whose scores are parked instead of filtered
+    const int warm_nblocks = max(0, min(C::WARM_BLOCKS, nblocks) - (G - 1));
 
     // flush the staging buffers of the lanes in `need` (lane mask) into the CTA lists
     auto flush_lanes = [&](unsigned need, bool blocking) {
@@ -475,7 +488,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     auto rare_path = [&](int Bg, float mn) {
         // Bg = block counter of lane group 0; this lane's block is Bg - h.  Only lanes of the last
         // lane group can satisfy mn <= tau (tau = -inf elsewhere).
-        if (mn <= tau) {
+        if (mn <= tau && Bg - h >= warm_nblocks) {  // blocks below warm_nblocks were parked and selected in phase B
             // usually exactly one of the 4 rows qualifies: peel minima until none is left under the threshold
             const uint32_t rel0 = (uint32_t)(Bg - h) * 4u;
             float a0 = o0, a1 = o1, a2 = o2, a3 = o3, m = mn;
@@ -504,7 +517,9 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
         }
     };
 
-    auto block_body = [&](int Bg) {
+    float* my_scratch = warm_scratch + (((size_t)blockIdx.x * QW + ql) * C::WARPS + w) * C::WARM_ROWS;
+
+    auto block_body = [&](int Bg, auto warm_tag) {
         const uint4 cw = lds128(plane + coff);
         coff += 16u;
         if (coff == (uint32_t)C::PLANE_RING_BYTES) coff = 0u;
@@ -521,24 +536,79 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
         B2_LOOKUP4(s2, r2, cw.z)
         B2_LOOKUP4(s3, r3, cw.w)
         o0 = s0; o1 = s1; o2 = s2; o3 = s3;
-        const float mn = fminf(fminf(s0, s1), fminf(s2, s3));
-        if (__any_sync(0xffffffffu, mn <= tau)) rare_path(Bg, mn);
+        if constexpr (decltype(warm_tag)::value) {
+            // warm-up rows: park the raw scores (one 16-byte store), no filtering
+            const int Bh = Bg - (G - 1);
+            if (last_group && (unsigned)Bh < (unsigned)warm_nblocks)
+                *reinterpret_cast<float4*>(my_scratch + Bh * 4) = make_float4(s0, s1, s2, s3);
+        } else {
+            const float mn = fminf(fminf(s0, s1), fminf(s2, s3));
+            if (__any_sync(0xffffffffu, mn <= tau)) rare_path(Bg, mn);
+        }
     };
 
-    int Bg = 0, slot = 0;
+    int Bg = 0, slot = 0, st = 0;
     uint32_t phases = 0;  // bit s = parity to wait for on ring slot s
-    for (int st = 0; st < n_st; st++) {
+    auto next_stage = [&]() {
         const int next = (slot == C::RING_STAGES - 1) ? 0 : slot + 1;
         // the slot after the current one held stage st-2, which every lane group has left
         if (st + 1 < n_st) issue_stage(st + 1, next);
         mbar_wait(full_bar + 8 * slot, (phases >> slot) & 1u);
         phases ^= 1u << slot;
         slot = next;
+    };
+    // ---- phase A: warm-up stages, scores parked ----
+    for (; st < min(n_st, C::WARM_STAGES); st++) {
+        next_stage();
+#pragma unroll 4
+        for (int bb = 0; bb < C::STAGE_BLOCKS; bb++, Bg++) block_body(Bg, std::true_type{});
+    }
+    // ---- phase B: the CTA selects the top-k of all parked rows in one dense pass ----
+    if (lane == 0) {
+        warm_valid[w] = min((uint32_t)warm_nblocks * 4u, nrel);
+        warm_idbase[w] = idbase;
+    }
+    __threadfence();  // parked scores visible to the selecting warps
+    asm volatile("bar.sync 1, %0;" ::"r"(C::WARPS * 32) : "memory");
+    for (int qq = w; qq < QW; qq += C::WARPS) {
+        const float* qs = warm_scratch + ((size_t)blockIdx.x * QW + qq) * C::WARPS * C::WARM_ROWS;
+        const uint32_t L = lists + (uint32_t)qq * (KP * 8);
+        int scnt = 0;  // records staged in this warp's staging area (used as one flat buffer here)
+        auto sflush = [&]() {
+            for (int off = 0; off < scnt; off += 32)
+                warp_flush(L, locks + qq, tau_key + qq, staging_w + (uint32_t)off * 8u, min(32, scnt - off), k);
+            scnt = 0;
+        };
+        for (int p0 = 0; p0 < C::WARPS * C::WARM_ROWS; p0 += 32) {
+            const int p = p0 + lane, ws = p / C::WARM_ROWS, off = p - ws * C::WARM_ROWS;
+            bool pass = false;
+            unsigned long long key = 0;
+            if ((uint32_t)off < warm_valid[ws]) {
+                float sc = __ldcg(qs + p);
+                sc = clamp < sc ? clamp : sc;
+                key = make_key(__float_as_uint(sc) | 0x80000000u, warm_idbase[ws] + (uint32_t)off);
+                pass = key < tau_key[qq];
+            }
+            const unsigned msk = __ballot_sync(0xffffffffu, pass);
+            if (msk) {
+                if (pass) sts64(staging_w + (uint32_t)(scnt + __popc(msk & ((1u << lane) - 1))) * 8u, key);
+                scnt += __popc(msk);
+                __syncwarp();
+                if (scnt > 32) sflush();
+            }
+        }
+        sflush();
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(C::WARPS * 32) : "memory");
+    // ---- phase C: stream the rest against the thresholds ----
+    for (; st < n_st; st++) {
+        next_stage();
         refresh_tau();
 #pragma unroll 4
-        for (int bb = 0; bb < C::STAGE_BLOCKS; bb++, Bg++) block_body(Bg);
+        for (int bb = 0; bb < C::STAGE_BLOCKS; bb++, Bg++) block_body(Bg, std::false_type{});
     }
-    for (int d = 0; d < G - 1; d++, Bg++) block_body(Bg);  // drain the lane-group pipeline
+    refresh_tau();
+    for (int d = 0; d < G - 1; d++, Bg++) block_body(Bg, std::false_type{});  // drain the lane-group pipeline
 
     // ---- flush what is still staged, then emit the CTA's sorted lists ----
     flush_lanes(__ballot_sync(0xffffffffu, last_group && cnt > 0), true);
@@ -821,7 +891,8 @@ void scan_plan(int sm_count, long long qgroups, long long n_granules, int* n_ful
 
 template <int G, int WARPS_>
 static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
-                       int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
+                       int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys,
+                       float* warm_scratch) {
     using C = ScanCfg<G, WARPS_>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -831,26 +902,34 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
     const long long n_gran = (n_rows + 63) / 64;
     const unsigned grid = (unsigned)(n_full + (qgroups - n_full) * tail_s);
     adc_scan_topk_kernel<G, WARPS_><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
-        codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, ctx->d_err);
+        codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, ctx->d_err);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;
 }
 
+// floats of warm-up scratch the scan needs for a given plan (per CTA: 32 lanes' worth of queries x WARPS x 128 rows)
+size_t scan_warm_scratch_floats(int M, long long qgroups, int n_full, int tail_s) {
+    const long long grid = n_full + (qgroups - n_full) * tail_s;
+    return (size_t)grid * (size_t)(128 / M) * 16 * 128;
+}
+
 template <int G>
 static int scan_dispatch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
-                         int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
-    return scan_launch<G, 16>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
+                         int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys,
+                         float* warm_scratch) {
+    return scan_launch<G, 16>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
 }
 
 int launch_adc_scan_topk(Ctx* ctx, int M, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
-                         int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys) {
+                         int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys,
+                         float* warm_scratch) {
     if (k < 1 || k > KP) B2_FAIL(-4, "fused ADC top-k supports 1 <= k <= 128");
     switch (M) {
-        case 4: return scan_dispatch<1>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
-        case 8: return scan_dispatch<2>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
-        case 16: return scan_dispatch<4>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
-        case 32: return scan_dispatch<8>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys);
+        case 4: return scan_dispatch<1>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
+        case 8: return scan_dispatch<2>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
+        case 16: return scan_dispatch<4>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
+        case 32: return scan_dispatch<8>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
         default: B2_FAIL(-4, "fast ADC scan supports M in {4, 8, 16, 32}");
     }
 }
