@@ -12,20 +12,27 @@ namespace b200nn {
 __global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, int L, long long nq, int k,
                                   long long list_stride, float* __restrict__ out_dist_f, int* __restrict__ out_dist_i,
                                   unsigned long long* __restrict__ out_id, unsigned long long* __restrict__ out_key) {
-    const int lane = threadIdx.x & 31;
-    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    extern __shared__ unsigned long long s_keys[];  // [warps][L*k]: the query's lists, staged once
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + w;
     if (q >= nq) return;
+    unsigned long long* sk = s_keys + (size_t)w * L * k;
     const unsigned long long* base = keys + q * k;
+    for (int e = lane; e < L * k; e += 32) {
+        const int l = e / k, j = e - l * k;
+        sk[e] = base[(long long)l * list_stride + j];
+    }
+    __syncwarp();
     int real = 0;
     for (int e = lane; e < L * k; e += 32) {
         const int l = e / k, j = e - l * k;
-        const unsigned long long key = base[(long long)l * list_stride + j];
+        const unsigned long long key = sk[e];
         if (key == KEY_MAX) continue;
         real++;
         int rank = j;
         for (int l2 = 0; l2 < L; l2++) {
             if (l2 == l) continue;
-            const unsigned long long* o = base + (long long)l2 * list_stride;
+            const unsigned long long* o = sk + l2 * k;
             int lo = 0, hi = k;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -53,12 +60,15 @@ __global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, i
     }
 }
 
-
 int launch_topk_merge(Ctx* ctx, const unsigned long long* keys, int L, long long nq, int k, long long list_stride,
                       float* out_dist_f, int* out_dist_i, unsigned long long* out_id, unsigned long long* out_key) {
     if (nq <= 0) return 0;
-    const int warps = 4;
-    topk_merge_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, 0, ctx->stream>>>(
+    int warps = 4;
+    while (warps > 1 && (size_t)warps * L * k * 8 > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * L * k * 8;
+    if (smem > 200 * 1024) B2_FAIL(-4, "topk_merge: too many lists x k for one warp's shared memory");
+    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_merge_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, smem, ctx->stream>>>(
         keys, L, nq, k, list_stride, out_dist_f, out_dist_i, out_id, out_key);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());

@@ -58,6 +58,7 @@ class ShardedPQ:
     def __init__(self, dist_module, rank: int, world: int, local_search, merge):
         self.dist, self.rank, self.world = dist_module, rank, world
         self.local_search, self.merge = local_search, merge
+        self._gathered = {}
 
     def search(self, q, k: int):
         import torch
@@ -65,7 +66,9 @@ class ShardedPQ:
         if self.world == 1:
             return self.merge(keys_local.unsqueeze(0))
         nq, kk = keys_local.shape
-        gathered = torch.empty((self.world * nq, kk), dtype=keys_local.dtype, device=keys_local.device)
+        gathered = self._gathered.get((nq, kk))
+        if gathered is None:
+            gathered = self._gathered[(nq, kk)] = torch.empty((self.world * nq, kk), dtype=keys_local.dtype, device=keys_local.device)
         self.dist.all_gather_into_tensor(gathered, keys_local)  # the single collective of the path
         return self.merge(gathered.view(self.world, nq, kk))
 
@@ -74,11 +77,22 @@ def make_gpu_sharded(ctx, index, dist_module, rank: int, world: int, id_base: in
     """Wire a ShardedPQ to the CUDA library for torch CUDA tensors."""
     import torch
 
+    bufs = {}
+
+    def _buffers(nq, k, device):
+        key = (nq, k)
+        if key not in bufs:  # reused across steps: no allocator traffic inside the timed region
+            bufs[key] = dict(keys=torch.empty((nq, k), dtype=torch.int64, device=device),
+                             dist=torch.empty((nq, k), dtype=torch.float32, device=device),
+                             ids=torch.empty((nq, k), dtype=torch.int64, device=device),
+                             mdist=torch.empty((nq, k), dtype=torch.float32, device=device),
+                             mids=torch.empty((nq, k), dtype=torch.int64, device=device))
+        return bufs[key]
+
     def local_search(q, k):
         nq = q.shape[0]
-        keys = torch.empty((nq, k), dtype=torch.int64, device=q.device)
-        dist = torch.empty((nq, k), dtype=torch.float32, device=q.device)
-        ids = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        b = _buffers(nq, k, q.device)
+        keys, dist, ids = b["keys"], b["dist"], b["ids"]
         index.search_dev(q.data_ptr(), nq, k, nprobe, dist.data_ptr(), ids.data_ptr(), keys.data_ptr(), id_base)
         local_search.last = (dist, ids)
         return keys
@@ -87,8 +101,8 @@ def make_gpu_sharded(ctx, index, dist_module, rank: int, world: int, id_base: in
         L, nq, k = keys_all.shape
         if L == 1 and hasattr(local_search, "last"):
             return local_search.last
-        dist = torch.empty((nq, k), dtype=torch.float32, device=keys_all.device)
-        ids = torch.empty((nq, k), dtype=torch.int64, device=keys_all.device)
+        b = _buffers(nq, k, keys_all.device)
+        dist, ids = b["mdist"], b["mids"]
         ctx.topk_merge_dev(keys_all.data_ptr(), L, nq, k, dist.data_ptr(), ids.data_ptr())
         return dist, ids
 
