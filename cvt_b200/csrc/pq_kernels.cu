@@ -304,7 +304,7 @@ struct ScanCfg {
     static constexpr int SB = (G == 1) ? 8 : (G == 2 ? 24 : 32);
     // try to merge once half a buffer is staged (measured: merging much earlier costs more in merges
     // than the fresher threshold saves in candidates)
-    static constexpr int SOFT = SB / 2;
+    static constexpr int SOFT = (G == 1) ? 4 : 10;  // measured flat optimum 8..12 (B200NN_SOFT overrides for tuning)
     static constexpr int STAGING_BYTES = QW * SB * 8;          // per warp
     static constexpr int LIST_BYTES = QW * KP * 8;
     // Warm-up: the first WARM_STAGES stages of every warp are not filtered at all -- their raw scores are
@@ -348,6 +348,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                      unsigned long long* __restrict__ out_keys,  // [slice][qgroups*QW][k]
                      long long q_stride_total,                   // qgroups*QW
                      float* __restrict__ warm_scratch,           // [grid][QW][WARPS][WARM_ROWS] raw scores of the warm-up rows
+                     int soft_thr,                               // staged records at which a warp tries to merge
                      int* __restrict__ err_flag) {
     using C = ScanCfg<G, WARPS_>;
     constexpr int QW = C::QW;
@@ -509,7 +510,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                 m = fminf(fminf(a0, a1), fminf(a2, a3));
             } while (m <= tau && m < __int_as_float(0x7f800000));
         }
-        const unsigned soft = __ballot_sync(0xffffffffu, cnt >= C::SOFT);
+        const unsigned soft = __ballot_sync(0xffffffffu, cnt >= soft_thr);
         if (soft) {
             const unsigned hard = __ballot_sync(0xffffffffu, cnt > C::SB - 4);
             if (hard) flush_lanes(hard, true);
@@ -901,8 +902,10 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
     }
     const long long n_gran = (n_rows + 63) / 64;
     const unsigned grid = (unsigned)(n_full + (qgroups - n_full) * tail_s);
+    int soft = C::SOFT;
+    if (const char* e = getenv("B200NN_SOFT")) soft = std::max(1, std::min(C::SB - 4, atoi(e)));
     adc_scan_topk_kernel<G, WARPS_><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
-        codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, ctx->d_err);
+        codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft, ctx->d_err);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;
