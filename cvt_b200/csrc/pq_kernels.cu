@@ -7,6 +7,7 @@
 // __fsub_rn/__fmul_rn/__fadd_rn so nothing is contracted into FMAs; every ADC score is the
 // sequential fp32 sum over m = 0..M-1 starting from 0.0f (IVFOPQ.cpp:302-306).  Codes, LUTs and
 // scores are therefore bit-identical to the reference's.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -338,7 +339,7 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
 // last wave) are split into tail_s row slices so that the last wave also fills the machine.  Every
 // (query, CTA) pair pays a top-k warm-up of ~k(1 + ln(rows/k)) insertions, so slices are used only
 // where they buy balance.
-template <int G, int WARPS_>
+template <int G, int WARPS_, bool STATS>
 __global__ void __launch_bounds__(WARPS_ * 32, 1)
 adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                      const float* __restrict__ lut_scan,    // [qgroups][32768]
@@ -349,6 +350,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                      long long q_stride_total,                   // qgroups*QW
                      float* __restrict__ warm_scratch,           // [grid][QW][WARPS][WARM_ROWS] raw scores of the warm-up rows
                      int soft_thr,                               // staged records at which a warp tries to merge
+                     unsigned long long* __restrict__ stats,     // STATS builds only (B200NN_SCAN_STATS): counters, see scan_launch
                      int* __restrict__ err_flag) {
     using C = ScanCfg<G, WARPS_>;
     constexpr int QW = C::QW;
@@ -356,6 +358,10 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int h = lane / QW, ql = lane - h * QW;
     const bool last_group = (h == G - 1);
+    unsigned st_ev = 0, st_cand = 0, st_try = 0, st_got = 0, st_hard = 0, st_candB = 0, st_peel = 0;
+    unsigned long long t_0 = 0, t_a = 0, t_b1 = 0, t_b = 0, t_b2 = 0;
+    auto now = [&]() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (STATS) t_0 = now();
     long long qg;
     int slice, n_slices;
     if ((int)blockIdx.x < n_full) { qg = blockIdx.x; slice = 0; n_slices = 1; }
@@ -477,7 +483,8 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                 if (lane == 0) got = (atomicCAS(locks + qsel, 0, 1) == 0);
                 got = __shfl_sync(0xffffffffu, got, 0);
                 if (got && lane == 0) __threadfence_block();
-            }
+                if (STATS) { st_try++; st_got += got; }
+            } else if (STATS) st_hard++;
             if (got) {
                 warp_flush(lists + (uint32_t)qsel * (KP * 8), locks + qsel, tau_key + qsel,
                            staging_w + (uint32_t)qsel * (C::SB * 8), nb, k, /*lock_held=*/!blocking);
@@ -503,8 +510,10 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                     if (s < tsc || make_key(ord, id) < tkey) {
                         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(my_staging + (uint32_t)cnt * 8u), "r"(id), "r"(ord) : "memory");
                         cnt++;
+                        if (STATS) st_cand++;
                     }
                 }
+                if (STATS) st_peel++;
                 const float inf = __int_as_float(0x7f800000);
                 a0 = (j == 0) ? inf : a0; a1 = (j == 1) ? inf : a1; a2 = (j == 2) ? inf : a2; a3 = (j == 3) ? inf : a3;
                 m = fminf(fminf(a0, a1), fminf(a2, a3));
@@ -544,7 +553,10 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                 *reinterpret_cast<float4*>(my_scratch + Bh * 4) = make_float4(s0, s1, s2, s3);
         } else {
             const float mn = fminf(fminf(s0, s1), fminf(s2, s3));
-            if (__any_sync(0xffffffffu, mn <= tau)) rare_path(Bg, mn);
+            if (__any_sync(0xffffffffu, mn <= tau)) {
+                if (STATS) st_ev++;
+                rare_path(Bg, mn);
+            }
         }
     };
 
@@ -570,37 +582,104 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
         warm_idbase[w] = idbase;
     }
     __threadfence();  // parked scores visible to the selecting warps
+    if (STATS) t_a = now();
     asm volatile("bar.sync 1, %0;" ::"r"(C::WARPS * 32) : "memory");
-    for (int qq = w; qq < QW; qq += C::WARPS) {
-        const float* qs = warm_scratch + ((size_t)blockIdx.x * QW + qq) * C::WARPS * C::WARM_ROWS;
-        const uint32_t L = lists + (uint32_t)qq * (KP * 8);
-        int scnt = 0;  // records staged in this warp's staging area (used as one flat buffer here)
-        auto sflush = [&]() {
-            for (int off = 0; off < scnt; off += 32)
-                warp_flush(L, locks + qq, tau_key + qq, staging_w + (uint32_t)off * 8u, min(32, scnt - off), k);
-            scnt = 0;
-        };
-        for (int p0 = 0; p0 < C::WARPS * C::WARM_ROWS; p0 += 32) {
-            const int p = p0 + lane, ws = p / C::WARM_ROWS, off = p - ws * C::WARM_ROWS;
-            bool pass = false;
-            unsigned long long key = 0;
-            if ((uint32_t)off < warm_valid[ws]) {
-                float sc = __ldcg(qs + p);
+    if (STATS) t_b1 = now();
+    // One warp per query holds the query's parked scores in registers (TOT/32 per lane) and finds the exact
+    // k-th smallest record by bisection on the score bits (scores are >= +0, so their bit patterns order like
+    // the values) and, only if the k-th score is tied, on the ids; the k survivors are rank-sorted straight
+    // into the (still empty) list.  ~30 rounds of register compares instead of ~15 serialised list merges.
+    {
+        static_assert(C::WARM_ROWS == 128, "slot -> (warp, row) mapping below assumes 128 parked rows per warp");
+        constexpr int TOT = C::WARPS * C::WARM_ROWS;  // parked slots per query
+        constexpr int E = TOT / 32;                   // slots per lane: slot p = i*32 + lane -> warp i/4, row (i%4)*32 + lane
+        for (int qq = w; qq < QW; qq += C::WARPS) {
+            const float* qs = warm_scratch + ((size_t)blockIdx.x * QW + qq) * TOT;
+            const uint32_t L = lists + (uint32_t)qq * (KP * 8);
+            constexpr uint32_t NONE = 0xFFFFFFFFu;  // above every score pattern
+            uint32_t x[E];
+            uint32_t n_valid = 0, vmin = NONE, vmax = 0;
+#pragma unroll
+            for (int i = 0; i < E; i++) {
+                const uint32_t off = (uint32_t)((i & 3) * 32 + lane);
+                const bool valid = off < warm_valid[i >> 2];
+                float sc = valid ? __ldcg(qs + i * 32 + lane) : 0.0f;
                 sc = clamp < sc ? clamp : sc;
-                key = make_key(__float_as_uint(sc) | 0x80000000u, warm_idbase[ws] + (uint32_t)off);
-                pass = key < tau_key[qq];
+                x[i] = valid ? __float_as_uint(sc) : NONE;
+                n_valid += valid ? 1u : 0u;
+                if (valid) { vmin = min(vmin, x[i]); vmax = max(vmax, x[i]); }
             }
-            const unsigned msk = __ballot_sync(0xffffffffu, pass);
-            if (msk) {
-                if (pass) sts64(staging_w + (uint32_t)(scnt + __popc(msk & ((1u << lane) - 1))) * 8u, key);
-                scnt += __popc(msk);
-                __syncwarp();
-                if (scnt > 32) sflush();
+            n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+            vmin = __reduce_min_sync(0xffffffffu, vmin);
+            vmax = __reduce_max_sync(0xffffffffu, vmax);
+            const uint32_t kk = min((uint32_t)k, n_valid);
+            if (kk == 0) continue;  // warp-uniform
+            // smallest v with #(x <= v) >= kk
+            uint32_t lo = vmin, hi = vmax;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                uint32_t c = 0;
+#pragma unroll
+                for (int i = 0; i < E; i++) c += (x[i] <= mid) ? 1u : 0u;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= kk) hi = mid; else lo = mid + 1;
             }
+            const uint32_t v = lo;
+            uint32_t c_lt = 0, c_le = 0;
+#pragma unroll
+            for (int i = 0; i < E; i++) { c_lt += (x[i] < v) ? 1u : 0u; c_le += (x[i] <= v) ? 1u : 0u; }
+            c_lt = __reduce_add_sync(0xffffffffu, c_lt);
+            c_le = __reduce_add_sync(0xffffffffu, c_le);
+            uint32_t tmax = NONE;  // ties at v are kept while id <= tmax
+            if (c_le > kk) {       // tied k-th score: the smallest ids win (warp-uniform branch)
+                const uint32_t need = kk - c_lt;
+                uint32_t ilo = 0, ihi = NONE;
+                while (ilo < ihi) {
+                    const uint32_t mid = ilo + ((ihi - ilo) >> 1);
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int i = 0; i < E; i++)
+                        c += (x[i] == v && warm_idbase[i >> 2] + (uint32_t)((i & 3) * 32 + lane) <= mid) ? 1u : 0u;
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (c >= need) ihi = mid; else ilo = mid + 1;
+                }
+                tmax = ilo;
+            }
+            // compact the kk survivors into this warp's staging area
+            uint32_t ns = 0;
+#pragma unroll
+            for (int i = 0; i < E; i++) {
+                const uint32_t id = warm_idbase[i >> 2] + (uint32_t)((i & 3) * 32 + lane);
+                const bool pass = x[i] < v || (x[i] == v && id <= tmax);
+                const unsigned msk = __ballot_sync(0xffffffffu, pass);
+                if (pass) sts64(staging_w + (ns + __popc(msk & ((1u << lane) - 1))) * 8u, make_key(x[i] | 0x80000000u, id));
+                ns += __popc(msk);
+            }
+            if (STATS) st_candB += ns;
+            __syncwarp();
+            // rank sort into the list (keys are distinct)
+            unsigned long long c[KP / 32];
+            int rk[KP / 32];
+#pragma unroll
+            for (int t = 0; t < KP / 32; t++) {
+                c[t] = (uint32_t)(lane + 32 * t) < ns ? lds64(staging_w + (uint32_t)(lane + 32 * t) * 8u) : KEY_MAX;
+                rk[t] = 0;
+            }
+            for (uint32_t j = 0; j < ns; j++) {
+                const unsigned long long kj = lds64(staging_w + j * 8u);
+#pragma unroll
+                for (int t = 0; t < KP / 32; t++) rk[t] += (kj < c[t]) ? 1 : 0;
+            }
+#pragma unroll
+            for (int t = 0; t < KP / 32; t++)
+                if ((uint32_t)(lane + 32 * t) < ns) sts64(L + (uint32_t)rk[t] * 8u, c[t]);
+            __syncwarp();
+            if (lane == 0) tau_key[qq] = (ns >= (uint32_t)k) ? lds64(L + (uint32_t)(k - 1) * 8u) : KEY_MAX;
         }
-        sflush();
     }
+    if (STATS) t_b = now();
     asm volatile("bar.sync 1, %0;" ::"r"(C::WARPS * 32) : "memory");
+    if (STATS) t_b2 = now();
     // ---- phase C: stream the rest against the thresholds ----
     for (; st < n_st; st++) {
         next_stage();
@@ -617,6 +696,28 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     for (int i = threadIdx.x; i < QW * k; i += blockDim.x) {
         const int qq = i / k, j = i - qq * k;
         out_keys[((long long)slice * q_stride_total + qg * QW + qq) * k + j] = lds64(lists + (uint32_t)(qq * KP + j) * 8u);
+    }
+    if (STATS) {
+        const unsigned long long t_e = now();
+        auto wsum = [&](unsigned v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; };
+        const unsigned c_cand = wsum(st_cand), c_peel = wsum(st_peel);
+        if (lane == 0) {
+            atomicAdd(stats + 0, (unsigned long long)st_ev);
+            atomicAdd(stats + 1, (unsigned long long)c_cand);
+            atomicAdd(stats + 2, (unsigned long long)st_try);
+            atomicAdd(stats + 3, (unsigned long long)st_got);
+            atomicAdd(stats + 4, (unsigned long long)st_hard);
+            atomicAdd(stats + 5, (unsigned long long)st_candB);
+            atomicAdd(stats + 6, (unsigned long long)c_peel);
+            if (w == 0) {
+                atomicAdd(stats + 8, t_a - t_0);    // phase A (warp 0)
+                atomicAdd(stats + 9, t_b1 - t_a);   // wait at barrier 1
+                atomicAdd(stats + 10, t_b - t_b1);  // phase B
+                atomicAdd(stats + 11, t_b2 - t_b);  // wait at barrier 2
+                atomicAdd(stats + 12, t_e - t_b2);  // phase C + emit
+                atomicAdd(stats + 13, 1ull);
+            }
+        }
     }
 }
 
@@ -897,15 +998,41 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
     using C = ScanCfg<G, WARPS_>;
     static bool attr_set = false;
     if (!attr_set) {
-        B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
     const long long n_gran = (n_rows + 63) / 64;
     const unsigned grid = (unsigned)(n_full + (qgroups - n_full) * tail_s);
     int soft = C::SOFT;
     if (const char* e = getenv("B200NN_SOFT")) soft = std::max(1, std::min(C::SB - 4, atoi(e)));
-    adc_scan_topk_kernel<G, WARPS_><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
-        codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft, ctx->d_err);
+    if (getenv("B200NN_SCAN_STATS")) {  // development aid: counters of the candidate path, printed per launch
+        static bool attr_set_s = false;
+        if (!attr_set_s) {
+            B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+            attr_set_s = true;
+        }
+        unsigned long long* d_stats = nullptr;
+        unsigned long long hs[16];
+        B2_CUDA(cudaMalloc(&d_stats, sizeof(hs)));
+        B2_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(hs), ctx->stream));
+        adc_scan_topk_kernel<G, WARPS_, true><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
+            codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft,
+            d_stats, ctx->d_err);
+        B2_CUDA(cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+        B2_CUDA(cudaStreamSynchronize(ctx->stream));
+        B2_CUDA(cudaFree(d_stats));
+        const double nc = (double)std::max<unsigned long long>(1, hs[13]);
+        fprintf(stderr,
+                "[scan stats] grid %u rows %lld soft %d | events %llu cand %llu (per query-CTA %.1f) peel %llu | try %llu got %llu hard %llu | "
+                "phaseB cand %llu | per-CTA us: A %.1f bar1 %.1f B %.1f bar2 %.1f C %.1f\n",
+                grid, n_rows, soft, hs[0], hs[1], (double)hs[1] / ((double)grid * C::QW), hs[6], hs[2], hs[3], hs[4], hs[5],
+                hs[8] / nc * 1e-3, hs[9] / nc * 1e-3, hs[10] / nc * 1e-3, hs[11] / nc * 1e-3, hs[12] / nc * 1e-3);
+        ctx->launches++;
+        return 0;
+    }
+    adc_scan_topk_kernel<G, WARPS_, false><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
+        codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft,
+        nullptr, ctx->d_err);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;
