@@ -48,33 +48,104 @@ def merge_keys_host(keys_all: np.ndarray, k: int) -> np.ndarray:
     return np.sort(flat, axis=1)[:, :k]
 
 
+def wave_split(nq: int, queries_per_cta: int, sm_count: int) -> list[tuple[int, int]]:
+    """Query chunks for the overlapped exchange: the scan runs one CTA per group of `queries_per_cta`
+    queries and one CTA per SM, so the first chunk is the whole waves of the batch and the second the
+    partial last wave (which the scan splits into row slices).  While the second chunk is scanned, the
+    first chunk's top-k records are already being gathered and merged.  One chunk when the batch has
+    no whole wave or no remainder."""
+    groups = -(-nq // queries_per_cta)
+    first = (groups // sm_count) * sm_count * queries_per_cta
+    if first <= 0 or first >= nq:
+        return [(0, nq)]
+    return [(0, first), (first, nq)]
+
+
 class ShardedPQ:
     """Distributed search over per-rank PQIndex shards.
 
     `local_search(q, k) -> keys [nq, k] (uint64 tensor, ascending)` and `merge(keys_all [L,nq,k]) ->
     (dist, ids)` are injectable so that the exchange logic runs under gloo on CPU in the tests;
-    on GPUs they are the C-ABI calls (pq_search_dev with out_key, topk_merge_dev)."""
+    on GPUs they are the C-ABI calls (pq_search_dev with out_key, topk_merge_dev).
 
-    def __init__(self, dist_module, rank: int, world: int, local_search, merge):
+    The collective stays ONE all-gather of [nq, k] records per rank; with `split` it is issued in
+    query chunks (same total payload) so that a chunk's gather + merge runs on `side` (a second
+    stream) underneath the scan of the next chunk.  Chunked calls pass rows=(lo, hi, nq) to both
+    callbacks; `assemble(parts)` turns the per-chunk results into the [nq, k] result."""
+
+    def __init__(self, dist_module, rank: int, world: int, local_search, merge, split=None, side=None, assemble=None):
         self.dist, self.rank, self.world = dist_module, rank, world
         self.local_search, self.merge = local_search, merge
+        self.split, self.side, self.assemble = split, side, assemble
         self._gathered = {}
 
-    def search(self, q, k: int):
+    def _exchange(self, keys_local, **rows):
         import torch
-        keys_local = self.local_search(q, k)  # [nq, k] int64 view of uint64 keys
-        if self.world == 1:
-            return self.merge(keys_local.unsqueeze(0))
         nq, kk = keys_local.shape
-        gathered = self._gathered.get((nq, kk))
+        tag = (rows.get("rows", (0,))[0], nq, kk)
+        gathered = self._gathered.get(tag)
         if gathered is None:
-            gathered = self._gathered[(nq, kk)] = torch.empty((self.world * nq, kk), dtype=keys_local.dtype, device=keys_local.device)
+            gathered = self._gathered[tag] = torch.empty((self.world * nq, kk), dtype=keys_local.dtype, device=keys_local.device)
         self.dist.all_gather_into_tensor(gathered, keys_local)  # the single collective of the path
-        return self.merge(gathered.view(self.world, nq, kk))
+        return self.merge(gathered.view(self.world, nq, kk), **rows)
+
+    def search(self, q, k: int):
+        nq = q.shape[0]
+        if self.world == 1:
+            return self.merge(self.local_search(q, k).unsqueeze(0))  # [nq, k] int64 view of uint64 keys
+        chunks = self.split(nq) if self.split is not None else [(0, nq)]
+        if len(chunks) == 1:
+            return self._exchange(self.local_search(q, k))
+        parts = [None] * len(chunks)
+        for ci, (lo, hi) in enumerate(chunks):
+            rows = (lo, hi, nq)
+            keys_c = self.local_search(q[lo:hi], k, rows=rows)
+
+            def exchange(ci=ci, keys_c=keys_c, rows=rows):
+                parts[ci] = self._exchange(keys_c, rows=rows)
+
+            if self.side is not None:
+                self.side.run(exchange)  # after everything queued so far; the caller's stream goes on with the next chunk
+            else:
+                exchange()
+        if self.side is not None:
+            self.side.join()
+        if self.assemble is not None:
+            return self.assemble(parts)
+        import torch
+        return tuple(torch.cat([torch.as_tensor(p[j]) for p in parts]) for j in range(2))
 
 
-def make_gpu_sharded(ctx, index, dist_module, rank: int, world: int, id_base: int, nprobe: int = 1):
-    """Wire a ShardedPQ to the CUDA library for torch CUDA tensors."""
+class _SideStream:
+    """Runs the exchange of a finished chunk on a second CUDA stream (torch + the library's context)."""
+
+    def __init__(self, ctx, device):
+        import torch
+        self.torch, self.ctx = torch, ctx
+        self.stream = torch.cuda.Stream(device=device)
+        self.ev = torch.cuda.Event()
+
+    def run(self, fn):
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        if cur.cuda_stream == 0:
+            raise RuntimeError("overlapped exchange needs a non-default current stream shared with the context (ctx.set_stream)")
+        self.ev.record(cur)
+        self.stream.wait_event(self.ev)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        try:
+            with torch.cuda.stream(self.stream):
+                fn()
+        finally:
+            self.ctx.set_stream(cur.cuda_stream)
+
+    def join(self):
+        self.torch.cuda.current_stream().wait_stream(self.stream)
+
+
+def make_gpu_sharded(ctx, index, dist_module, rank: int, world: int, id_base: int, nprobe: int = 1, overlap: bool = True):
+    """Wire a ShardedPQ to the CUDA library for torch CUDA tensors.  The caller's current torch stream
+    must be the stream the context launches on (ctx.set_stream)."""
     import torch
 
     bufs = {}
@@ -89,21 +160,29 @@ def make_gpu_sharded(ctx, index, dist_module, rank: int, world: int, id_base: in
                              mids=torch.empty((nq, k), dtype=torch.int64, device=device))
         return bufs[key]
 
-    def local_search(q, k):
-        nq = q.shape[0]
+    def local_search(q, k, rows=None):
+        lo, hi, nq = rows if rows is not None else (0, q.shape[0], q.shape[0])
         b = _buffers(nq, k, q.device)
-        keys, dist, ids = b["keys"], b["dist"], b["ids"]
-        index.search_dev(q.data_ptr(), nq, k, nprobe, dist.data_ptr(), ids.data_ptr(), keys.data_ptr(), id_base)
-        local_search.last = (dist, ids)
+        keys, dist, ids = b["keys"][lo:hi], b["dist"][lo:hi], b["ids"][lo:hi]
+        index.search_dev(q.data_ptr(), hi - lo, k, nprobe, dist.data_ptr(), ids.data_ptr(), keys.data_ptr(), id_base)
+        local_search.last = (b["dist"], b["ids"])
         return keys
 
-    def merge(keys_all):
-        L, nq, k = keys_all.shape
+    def merge(keys_all, rows=None):
+        L, nq_c, k = keys_all.shape
         if L == 1 and hasattr(local_search, "last"):
             return local_search.last
+        lo, hi, nq = rows if rows is not None else (0, nq_c, nq_c)
         b = _buffers(nq, k, keys_all.device)
         dist, ids = b["mdist"], b["mids"]
-        ctx.topk_merge_dev(keys_all.data_ptr(), L, nq, k, dist.data_ptr(), ids.data_ptr())
+        ctx.topk_merge_dev(keys_all.data_ptr(), L, nq_c, k, dist[lo:hi].data_ptr(), ids[lo:hi].data_ptr())
         return dist, ids
 
-    return ShardedPQ(dist_module, rank, world, local_search, merge)
+    split = side = None
+    # the fused flat scan (K = 1, 256 centroids, M in {4, 8, 16, 32}) runs 128/M queries per CTA, one CTA per SM
+    if overlap and world > 1 and nprobe == 1 and index.K == 1 and index.ksub == 256 and index.M in (4, 8, 16, 32):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        qpc, sms = 128 // index.M, torch.cuda.get_device_properties(dev).multi_processor_count
+        split = lambda nq: wave_split(nq, qpc, sms)
+        side = _SideStream(ctx, dev)
+    return ShardedPQ(dist_module, rank, world, local_search, merge, split=split, side=side, assemble=lambda parts: parts[-1])

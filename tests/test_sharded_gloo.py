@@ -25,6 +25,17 @@ def test_shard_bounds_cover_and_are_contiguous():
             assert all(hi - lo <= per for lo, hi in edges)
 
 
+def test_wave_split_whole_waves_then_remainder():
+    # batch 4096, 8 queries per CTA, 148 SMs: 512 groups = 3 whole waves (444 groups) + 68
+    assert sharded.wave_split(4096, 8, 148) == [(0, 3552), (3552, 4096)]
+    assert sharded.wave_split(1024, 8, 148) == [(0, 1024)]          # less than one wave
+    assert sharded.wave_split(148 * 8 * 2, 8, 148) == [(0, 2368)]    # whole waves only
+    assert sharded.wave_split(0, 8, 148) == [(0, 0)]
+    for nq in (1, 7, 1185, 5000, 16384):
+        ch = sharded.wave_split(nq, 4, 148)
+        assert ch[0][0] == 0 and ch[-1][1] == nq and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+
+
 def test_key_packing_orders_like_pairs():
     rng = np.random.Generator(np.random.PCG64(1))
     d = rng.standard_normal(5000).astype(np.float32)
@@ -54,19 +65,29 @@ def _worker(rank, world, port, ret):
         qr = orc.opq_reorder(c["q"], c["reorder"])
         lo, hi = sharded.shard_bounds(c["n"], world, rank)
 
-        def local_search(q, kk):
+        seen_rows = []
+
+        def local_search(q, kk, rows=None):
+            seen_rows.append(rows)
             D, I = orc.opq_search_flat(q.numpy(), c["coarse"][0], c["cb"], codes[lo:hi], kk, clamp=1.0)
             keys = sharded.pack_keys(D, I + lo)  # global ids = id_base + local row
             return torch.from_numpy(keys.view(np.int64))
 
-        def merge(keys_all):
+        def merge(keys_all, rows=None):
             m = sharded.merge_keys_host(keys_all.numpy().view(np.uint64), k)
             return sharded.unpack_keys(m)
 
+        Dref, Iref = orc.opq_search_flat(qr, c["coarse"][0], c["cb"], codes, k, clamp=1.0)
         sh = sharded.ShardedPQ(dist, rank, world, local_search, merge)
         D, I = sh.search(torch.from_numpy(qr), k)
-        Dref, Iref = orc.opq_search_flat(qr, c["coarse"][0], c["cb"], codes, k, clamp=1.0)
         ok = bool(np.array_equal(I, Iref) and np.array_equal(D.view(np.uint32), Dref.view(np.uint32)))
+        # the same exchange issued in query chunks (what the GPU path overlaps with the next chunk's scan)
+        nq = qr.shape[0]
+        cut = max(1, nq // 3)
+        sh2 = sharded.ShardedPQ(dist, rank, world, local_search, merge, split=lambda n: [(0, cut), (cut, n)])
+        D2, I2 = sh2.search(torch.from_numpy(qr), k)
+        ok = ok and seen_rows[-2:] == [(0, cut, nq), (cut, nq, nq)]
+        ok = ok and bool(np.array_equal(I2.numpy(), Iref) and np.array_equal(D2.numpy().view(np.uint32), Dref.view(np.uint32)))
         ret[rank] = ok
     finally:
         dist.destroy_process_group()
