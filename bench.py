@@ -8,8 +8,10 @@ Workload (default `cfg3`, BASELINE.json configs[2], the configuration the metric
 OPQ M=16 8-bit sub-codes, 1M x 128-d SIFT-shaped unit-norm vectors, flat (K=1) ADC scan, top-100
 (recall@10 reported), batch 4096, clamp threshold 1.0 as in the reference.  A "step" = one pass of
 the hot path over one query batch: rotate -> LUT build -> ADC scan + top-k -> slice merge
-[-> all-gather of shard top-k + merge when N > 1].  With N > 1 the SAME database is row-sharded
-over the ranks ("scaling": "strong"); the query batch is replicated.
+[-> all-gather of per-rank top-k + merge when N > 1].  With N > 1 the SAME database and batch are split
+over a (query chunk x row shard) grid of ranks ("scaling": "strong"): cvt_b200.sharded.plan_layout picks
+the grid (row shards = N is the plain row-sharded layout; --row-shards forces it), and when the planner
+picks something else the plain row-sharded layout is timed as well and reported under "row_sharded".
 
 Prints ONE JSON line on rank 0 (see README/DESIGN for the fields).
 """
@@ -234,6 +236,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries of the batch timed on the host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--row-shards", type=int, default=0, help="row shards R of the rank grid (0: planned; N: plain row sharding)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
@@ -285,13 +288,22 @@ def main():
 
     inputs = make_inputs(wl)
     db, q, perm, coarse, cb = inputs
-    lo, hi = sharded.shard_bounds(n, world, rank)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    R, Qc = (args.row_shards, world // max(1, args.row_shards)) if args.row_shards else sharded.plan_layout(world, n, B, M, k, sms)
+    if R < 1 or R * Qc != world:
+        raise SystemExit(f"bench.py: --row-shards {args.row_shards} must divide --gpus {world}")
     ctx = capi.Context(local_rank)
     ctx.set_stream(stream.cuda_stream)
-    index = capi.PQIndex.create(ctx, coarse, cb, perm=perm, clamp=1.0)
-    index.add(db[lo:hi])
-    sh = sharded.make_gpu_sharded(ctx, index, dist, rank, world, id_base=lo, nprobe=1,
-                                  overlap=os.environ.get("B200NN_OVERLAP", "") == "1")  # knob for A/B runs of the exchange (default: one plain gather)
+
+    def make_layout(row_shards):
+        r, _ = sharded.grid_coords(rank, row_shards)
+        s_lo, s_hi = sharded.shard_bounds(n, row_shards, r)
+        idx = capi.PQIndex.create(ctx, coarse, cb, perm=perm, clamp=1.0)
+        idx.add(db[s_lo:s_hi])
+        return idx, sharded.make_gpu_sharded(ctx, idx, dist, rank, world, id_base=s_lo, nprobe=1, row_shards=row_shards), s_lo, s_hi
+
+    index, sh, lo, hi = make_layout(R)
+    q_lo, q_hi, _ = sharded.query_chunk(B, Qc, sharded.grid_coords(rank, R)[1])
 
     q_pinned = torch.from_numpy(q).pin_memory()
     q_dev = q_pinned.to(dev)
@@ -304,6 +316,25 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed_steps(sh_, index_, steps):
+        """`steps` timed steps (CUDA events on the launching stream, L2 flushed before each, barrier +
+        synchronize on both sides) -> (ms per step = max over ranks, per-stage ms of this rank, result)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        stages = []
+        barrier()
+        for s_ in range(steps):
+            flush.zero_()  # evict L2 between timed iterations (outside the event pair)
+            ev[s_][0].record()
+            dd_, ii_ = sh_.search(q_dev, k)
+            ev[s_][1].record()
+            ev[s_][1].synchronize()
+            stages.append(index_.last_timing())
+        barrier()
+        total = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return float(total.item()) / steps, stages, (dd_, ii_)
 
     # ---- device-resident timing ("value"): inputs in HBM, CUDA events on the launching stream
     sampler = ClockSampler(local_rank)
@@ -324,53 +355,29 @@ def main():
             dd, ii = sh.search(q_dev, k)
         barrier()
     launches0 = ctx.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    stage_ms = []
-    barrier()
     t_wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush.zero_()  # evict L2 between timed iterations (outside the event pair)
-        ev[s][0].record()
-        dd, ii = sh.search(q_dev, k)
-        ev[s][1].record()
-        ev[s][1].synchronize()
-        stage_ms.append(index.last_timing())
-    barrier()
+    ms_per_step, stage_ms, (dd, ii) = timed_steps(sh, index, args.steps)
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
     qps = B / (ms_per_step * 1e-3)
     result_ids = ii.cpu().numpy()
     result_d = dd.cpu().numpy()
-    chunks = sh.split(B) if (world > 1 and sh.split is not None) else [(0, B)]
-    if len(chunks) > 1:
-        # the timed steps overlap the exchange of query chunk c with the scan of chunk c+1; the per-stage
-        # times (and the scan's roofline) are taken in a separate pass, one synchronised launch per chunk
-        tk = torch.empty((B, k), dtype=torch.int64, device=dev)
-        td = torch.empty((B, k), dtype=torch.float32, device=dev)
-        ti = torch.empty((B, k), dtype=torch.int64, device=dev)
-        stage_ms = []
-        for _ in range(5):
-            flush.zero_()
-            acc = {}
-            for c_lo, c_hi in chunks:
-                index.search_dev(q_dev[c_lo:c_hi].data_ptr(), c_hi - c_lo, k, 1, td[c_lo:c_hi].data_ptr(), ti[c_lo:c_hi].data_ptr(),
-                                 tk[c_lo:c_hi].data_ptr(), lo)
-                torch.cuda.synchronize()
-                for kk, v in index.last_timing().items():
-                    acc[kk] = acc.get(kk, 0.0) + v
-            stage_ms.append(acc)
-        # and the overlapped result must equal the plain one-gather path
-        plain = sharded.make_gpu_sharded(ctx, index, dist, rank, world, id_base=lo, nprobe=1, overlap=False)
-        pd, pi = plain.search(q_dev, k)
-        assert np.array_equal(pi.cpu().numpy(), result_ids) and np.array_equal(pd.cpu().numpy().view(np.uint32), result_d.view(np.uint32)), \
-            "overlapped exchange and plain exchange disagree"
     scan_ms = float(np.mean([t["scan_ms"] for t in stage_ms]))
+
+    # ---- the plain row-sharded layout (row shards = N, queries replicated) beside the planned grid
+    row_sharded = None
+    if world > 1 and R != world:
+        index_rs, sh_rs, lo_rs, hi_rs = make_layout(world)
+        for _ in range(args.warmup):
+            sh_rs.search(q_dev, k)
+        ms_rs, stages_rs, (d_rs, i_rs) = timed_steps(sh_rs, index_rs, args.steps)
+        assert np.array_equal(i_rs.cpu().numpy(), result_ids) and np.array_equal(d_rs.cpu().numpy().view(np.uint32), result_d.view(np.uint32)), \
+            "row-sharded layout and planned grid disagree"
+        scan_rs = float(np.mean([t["scan_ms"] for t in stages_rs]))
+        row_sharded = {"value": B / (ms_rs * 1e-3), "unit": "queries/s", "ms_per_step": ms_rs, "rows_per_gpu": hi_rs - lo_rs,
+                       "scan_kernel_ms": scan_rs, "roofline_frac": float(B) * (hi_rs - lo_rs) * M / (scan_rs * 1e-3) / 1e9 / measured_peak_hbm()[0]}
+        index_rs.close()
 
     # ---- end-to-end through the public C-ABI call with HOST buffers (H2D + D2H inside the timed region)
     def e2e_step():
@@ -401,7 +408,7 @@ def main():
         return 0
 
     peak, peak_src = measured_peak_hbm()
-    alg_bytes = float(B) * (hi - lo) * M  # every query "reads" every code byte of the shard once
+    alg_bytes = float(q_hi - q_lo) * (hi - lo) * M  # every query of this rank's chunk "reads" every code byte of its shard once
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
@@ -413,16 +420,20 @@ def main():
     line = {"metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (LUT sums) over u8 codes", "data": "synthetic",
-            "config": {"workload": wl["desc"], "n_rows": n, "rows_per_gpu": hi - lo, "dim": D, "M": M, "ksub": 256, "batch": B, "k": k,
-                       "nprobe": 1, "clamp": 1.0, "parallelism": (f"row-sharded x{world}, one all-gather of top-k keys" + (f", issued in {len(chunks)} query chunks {chunks} so a chunk's gather+merge overlaps the next chunk's scan" if len(chunks) > 1 else "")) if world > 1 else "single GPU",
+            "config": {"workload": wl["desc"], "n_rows": n, "rows_per_gpu": hi - lo, "queries_per_gpu": q_hi - q_lo, "dim": D, "M": M, "ksub": 256,
+                       "batch": B, "k": k, "nprobe": 1, "clamp": 1.0,
+                       "parallelism": (f"{R} row shard(s) x {Qc} query chunk(s) ({'planned' if not args.row_shards else 'forced'}), one all-gather of top-k keys"
+                                       if world > 1 else "single GPU"),
                        "l2": "256 MB buffer written between timed iterations (L2 flush)", "extra_untimed_warmup_steps_for_clock_sampling": extra_warm, "seeds": "SURVEY.md §8(d)"},
             "roofline": {"bound": "hbm", "kernel": "adc_scan_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms, "scan_launches_per_step": len(chunks),
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms, "scan_launches_per_step": 1,
                          "note": "algorithmic bytes = batch x shard rows x M; binding unit is the shared-memory gather pipe (DESIGN.md)"},
             "stage_ms": {kk: float(np.mean([t[kk] for t in stage_ms])) for kk in stage_ms[0]},
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(B * D * 4), "d2h_bytes_per_step": int(B * k * 12)},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall}
+    if row_sharded is not None:
+        line["row_sharded"] = row_sharded
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the unmodified reference on a bounded sample, + parity
     if world == 1 and not args.no_cpu_baseline:

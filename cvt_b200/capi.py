@@ -24,6 +24,7 @@ SYMBOLS = [
     "b200nn_pq_create", "b200nn_pq_load_model", "b200nn_pq_destroy", "b200nn_pq_set_clamp", "b200nn_pq_info",
     "b200nn_pq_rotate", "b200nn_pq_encode", "b200nn_pq_add", "b200nn_pq_add_dev", "b200nn_pq_add_rotated", "b200nn_pq_get_rows",
     "b200nn_pq_build_lut", "b200nn_pq_scores", "b200nn_pq_search", "b200nn_pq_search_dev", "b200nn_topk_merge_dev",
+    "b200nn_topk_merge_grid_dev", "b200nn_pq_scan_plan",
     "b200nn_pq_save_index", "b200nn_pq_load_index", "b200nn_pq_last_timing", "b200nn_pq_scan_bytes",
     "b200nn_sq_create", "b200nn_sq_destroy", "b200nn_sq_train_minmax", "b200nn_sq_encode", "b200nn_sq_decode",
     "b200nn_sq_encode_dev",
@@ -113,6 +114,22 @@ class Context:
     def topk_merge_dev(self, keys_dev: int, L: int, nq: int, k: int, out_dist_dev: int, out_id_dev: int):
         _check(load().b200nn_topk_merge_dev(self.h, C.c_void_p(keys_dev), C.c_int(L), C.c_size_t(nq), C.c_size_t(k),
                                             C.c_void_p(out_dist_dev), C.c_void_p(out_id_dev)), "topk_merge_dev")
+
+
+    def topk_merge_grid_dev(self, keys_dev: int, n_chunks: int, L: int, chunk_q: int, nq: int, k: int, out_dist_dev: int,
+                            out_id_dev: int):
+        _check(load().b200nn_topk_merge_grid_dev(self.h, C.c_void_p(keys_dev), C.c_int(n_chunks), C.c_int(L), C.c_size_t(chunk_q),
+                                                 C.c_size_t(nq), C.c_size_t(k), C.c_void_p(out_dist_dev), C.c_void_p(out_id_dev)),
+               "topk_merge_grid_dev")
+
+
+def scan_plan(sm_count: int, M: int, nq: int, n_rows: int):
+    """Host-only: the fused scan's work plan -> (n_full, n_tail, slices, desc[n_tail, 2, 4])."""
+    nf, nt, sl = C.c_int(), C.c_int(), C.c_int()
+    desc = np.zeros((max(1, sm_count), 2, 4), dtype=np.int32)
+    _check(load().b200nn_pq_scan_plan(C.c_int(sm_count), C.c_int(M), C.c_size_t(nq), C.c_size_t(n_rows), C.byref(nf), C.byref(nt),
+                                      C.byref(sl), _vp(desc), C.c_size_t(desc.size)), "pq_scan_plan")
+    return nf.value, nt.value, sl.value, desc[:nt.value]
 
 
 class PQIndex:

@@ -93,4 +93,16 @@ int b200nn_topk_merge_dev(b200nn_ctx_t ctx, const uint64_t* keys_dev, int L, siz
                              out_dist_dev, nullptr, (unsigned long long*)out_id_dev, nullptr);
 }
 
+// The all-gathered records of a (query chunk x row shard) grid of ranks: keys [n_chunks][L][chunk_q][k],
+// rank = chunk * L + shard; query q of the batch is row q % chunk_q of chunk q / chunk_q.  One launch.
+int b200nn_topk_merge_grid_dev(b200nn_ctx_t ctx, const uint64_t* keys_dev, int n_chunks, int L, size_t chunk_q, size_t nq,
+                               size_t k, float* out_dist_dev, uint64_t* out_id_dev) {
+    if (!ctx || !keys_dev || L < 1 || k < 1 || n_chunks < 1 || chunk_q < 1) B2_FAIL(B200NN_ERR_INVALID, "topk_merge_grid: bad arguments");
+    if (nq > (size_t)n_chunks * chunk_q) B2_FAIL(B200NN_ERR_INVALID, "topk_merge_grid: nq exceeds n_chunks * chunk_q");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    B2_CUDA(cudaSetDevice(ctx->c.device));
+    return launch_topk_merge(&ctx->c, (const unsigned long long*)keys_dev, L, (long long)nq, (int)k, (long long)(chunk_q * k),
+                             out_dist_dev, nullptr, (unsigned long long*)out_id_dev, nullptr);
+}
+
 }  // extern "C"

@@ -37,6 +37,10 @@ struct b200nn_pq {
     DevBuf<int> ws_probes, ws_list;
     DevBuf<unsigned char> ws_codes;
     DevBuf<unsigned long long> ws_keys, ws_keys2, ws_id;
+    // work plan of the fused scan, cached per (query groups, granules) shape
+    ScanPlan plan;
+    long long plan_qgroups = -1, plan_gran = -1;
+    DevBuf<int> plan_desc;
     float timing[4] = {0, 0, 0, 0};
 };
 
@@ -274,14 +278,20 @@ int search_dev_locked(b200nn_pq* p, const float* q_raw_dev, long long nq, int np
         if ((rc = launch_lut_build_scan(c, p->M, qr, nq, p->D, p->coarse.p, p->cb.p, p->ws_lut.p))) return rc;
         B2_CUDA(cudaEventRecord(ev[2], c->stream));
         const long long n_gran = (p->n + 63) / 64;
-        int n_full = 0, tail_s = 1;
-        scan_plan(c->sm_count, qgroups, n_gran, &n_full, &tail_s);
-        const int S = tail_s;
+        if (p->plan_qgroups != qgroups || p->plan_gran != n_gran) {  // plan + tail descriptors, cached per (batch, rows) shape
+            scan_plan(c->sm_count, qgroups, n_gran, &p->plan);
+            if ((rc = p->plan_desc.ensure(std::max<size_t>(8, p->plan.desc.size())))) return rc;
+            if (!p->plan.desc.empty())
+                B2_CUDA(cudaMemcpyAsync(p->plan_desc.p, p->plan.desc.data(), sizeof(int) * p->plan.desc.size(), cudaMemcpyHostToDevice, c->stream));
+            p->plan_qgroups = qgroups;
+            p->plan_gran = n_gran;
+        }
+        const int n_full = p->plan.n_full, n_tail = p->plan.n_tail, S = p->plan.slices;
         if ((rc = p->ws_keys.ensure((size_t)S * qgroups * QW * k))) return rc;
         if (S > 1)  // whole-shard CTAs write slice 0 only: the other slices of those queries stay empty (KEY_MAX)
             B2_CUDA(cudaMemsetAsync(p->ws_keys.p, 0xFF, (size_t)S * qgroups * QW * k * sizeof(unsigned long long), c->stream));
-        if ((rc = p->ws_warm.ensure(scan_warm_scratch_floats(p->M, qgroups, n_full, tail_s)))) return rc;
-        if ((rc = launch_adc_scan_topk(c, p->M, p->codesT.p, p->ws_lut.p, p->n, qgroups, n_full, tail_s, k, p->clamp,
+        if ((rc = p->ws_warm.ensure(scan_warm_scratch_floats(p->M, n_full, n_tail)))) return rc;
+        if ((rc = launch_adc_scan_topk(c, p->M, p->codesT.p, p->ws_lut.p, p->n, qgroups, n_full, n_tail, p->plan_desc.p, k, p->clamp,
                                        (uint32_t)id_base, p->ws_keys.p, p->ws_warm.p)))
             return rc;
         B2_CUDA(cudaEventRecord(ev[3], c->stream));
@@ -528,6 +538,24 @@ int b200nn_pq_last_timing(b200nn_pq_t p, float* ms4) {
 int b200nn_pq_scan_bytes(b200nn_pq_t p, uint64_t* code_bytes) {
     if (!p || !code_bytes) B2_FAIL(B200NN_ERR_INVALID, "NULL argument");
     *code_bytes = (uint64_t)p->n * p->M;
+    return 0;
+}
+
+// Host-only view of the fused scan's work plan (no device work): how a batch of `nq` queries over
+// `n_rows` rows of M-byte codes is cut into CTAs on a GPU with `sm_count` SMs.
+int b200nn_pq_scan_plan(int sm_count, int M, size_t nq, size_t n_rows, int* n_full, int* n_tail, int* slices, int32_t* desc,
+                        size_t desc_capacity) {
+    const int QW = scan_queries_per_cta(M);
+    if (sm_count < 1 || QW < 1 || 128 % M) B2_FAIL(B200NN_ERR_INVALID, "pq_scan_plan: need sm_count >= 1 and M in {4, 8, 16, 32}");
+    ScanPlan plan;
+    scan_plan(sm_count, ((long long)nq + QW - 1) / QW, ((long long)n_rows + 63) / 64, &plan);
+    if (n_full) *n_full = plan.n_full;
+    if (n_tail) *n_tail = plan.n_tail;
+    if (slices) *slices = plan.slices;
+    if (desc) {
+        if (desc_capacity < plan.desc.size()) B2_FAIL(B200NN_ERR_INVALID, "pq_scan_plan: desc buffer too small (8 ints per tail CTA)");
+        std::copy(plan.desc.begin(), plan.desc.end(), desc);
+    }
     return 0;
 }
 

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <type_traits>
+#include <vector>
 
 #include "pq_kernels.cuh"
 #include "topk.cuh"
@@ -334,18 +335,21 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
     S = __fadd_rn(S, lds_f32_off<65536>(__byte_perm(W, basereg, 0x7624)));                      \
     S = __fadd_rn(S, lds_f32_off<65536 + 128>(__byte_perm(W, basereg, 0x7634)));
 
-// Work decomposition: one CTA per (query group, row slice).  The first n_full query groups are
-// scanned whole by one CTA each (whole waves of one-CTA-per-SM); the remaining groups (the partial
-// last wave) are split into tail_s row slices so that the last wave also fills the machine.  Every
-// (query, CTA) pair pays a top-k warm-up of ~k(1 + ln(rows/k)) insertions, so slices are used only
-// where they buy balance.
+// Work decomposition: the first n_full query groups are scanned whole by one CTA each (whole waves
+// of one-CTA-per-SM).  The remaining groups (the partial last wave) form one linear stretch of
+// (group, granule) work that is cut into equal pieces, one per tail CTA, so that the last wave fills
+// the machine exactly whatever the group count is; a piece may straddle the boundary between two
+// groups, in which case the CTA runs two segments (own LUT, own top-k lists, own output slice).
+// Every (query, segment) pair pays a top-k warm-up of ~k(1 + ln(rows/k)) insertions, so pieces are
+// used only where they buy balance.  tail_desc holds two {group, slice, granule lo, granule hi}
+// records per tail CTA (scan_plan); the second is empty (lo >= hi) when the piece lies in one group.
 template <int G, int WARPS_, bool STATS>
 __global__ void __launch_bounds__(WARPS_ * 32, 1)
 adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                      const float* __restrict__ lut_scan,    // [qgroups][32768]
                      long long n_rows,                      // valid rows of this shard
                      long long n_granules,                  // ceil(n_rows / 64)
-                     int n_full, int tail_s, int k, float clamp, uint32_t id_base,
+                     int n_full, const int4* __restrict__ tail_desc, int k, float clamp, uint32_t id_base,
                      unsigned long long* __restrict__ out_keys,  // [slice][qgroups*QW][k]
                      long long q_stride_total,                   // qgroups*QW
                      float* __restrict__ warm_scratch,           // [grid][QW][WARPS][WARM_ROWS] raw scores of the warm-up rows
@@ -361,11 +365,6 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     unsigned st_ev = 0, st_cand = 0, st_try = 0, st_got = 0, st_hard = 0, st_candB = 0, st_peel = 0;
     unsigned long long t_0 = 0, t_a = 0, t_b1 = 0, t_b = 0, t_b2 = 0;
     auto now = [&]() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
-    if (STATS) t_0 = now();
-    long long qg;
-    int slice, n_slices;
-    if ((int)blockIdx.x < n_full) { qg = blockIdx.x; slice = 0; n_slices = 1; }
-    else { const int idx = (int)blockIdx.x - n_full; qg = n_full + idx / tail_s; slice = idx % tail_s; n_slices = tail_s; }
 
     // ---- carve shared memory: LUT at a 64 KB aligned window address, the rest around it ----
     const uint32_t base = smem_u32(dyn_smem);
@@ -393,8 +392,29 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     unsigned int* warm_valid = (unsigned int*)(generic_base + misc + 1700);   // [WARPS] parked rows per warp
     unsigned int* warm_idbase = (unsigned int*)(generic_base + misc + 1800);  // [WARPS] id of a warp's first row
 
+    // ---- barriers (once per CTA; their phases run on across segments) ----
+    if (threadIdx.x == 0) mbar_init(lut_bar, 1);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < C::RING_STAGES; s++) mbar_init(full_bar + 8 * s, 1);
+    }
+    mbar_fence_init();
+    uint32_t phases = 0;  // bit s = parity to wait for on ring slot s
+    const bool whole = (int)blockIdx.x < n_full;
+
+#pragma unroll 1
+    for (int seg = 0; seg < (whole ? 1 : 2); seg++) {
+    long long qg, g_lo, g_hi;
+    int slice;
+    if (whole) { qg = blockIdx.x; slice = 0; g_lo = 0; g_hi = n_granules; }
+    else {
+        const int4 d = __ldg(tail_desc + ((int)blockIdx.x - n_full) * 2 + seg);
+        if (seg > 0 && d.z >= d.w) break;  // the piece lies inside one group (CTA-uniform)
+        qg = d.x; slice = d.y; g_lo = d.z; g_hi = d.w;
+    }
+    if (STATS) { t_0 = now(); st_ev = st_cand = st_try = st_got = st_hard = st_candB = st_peel = 0; }
+
     // ---- this warp's stream of rows ----
-    const long long g_lo = (n_granules * slice) / n_slices, g_hi = (n_granules * (slice + 1)) / n_slices;
     const long long stages_total = (g_hi - g_lo) * (64 / C::STAGE_ROWS);
     const long long st_per_warp = (stages_total + C::WARPS - 1) / C::WARPS;
     const long long st_lo = min(stages_total, (long long)w * st_per_warp), st_hi = min(stages_total, st_lo + st_per_warp);
@@ -402,15 +422,9 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     const long long row0 = g_lo * 64 + st_lo * C::STAGE_ROWS;  // first row of the stream
     const int nblocks = n_st * C::STAGE_BLOCKS;
 
-    // ---- barriers, lists ----
-    if (threadIdx.x == 0) mbar_init(lut_bar, 1);
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < C::RING_STAGES; s++) mbar_init(full_bar + 8 * s, 1);
-    }
+    // ---- lists ----
     for (int i = threadIdx.x; i < QW * KP; i += blockDim.x) sts64(lists + (uint32_t)i * 8u, KEY_MAX);
     if (threadIdx.x < QW) { tau_key[threadIdx.x] = KEY_MAX; locks[threadIdx.x] = 0; }
-    mbar_fence_init();
     __syncthreads();
 
     // ---- LUT: 8 TMA bulk copies of 16 KB ----
@@ -439,7 +453,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     };
     if (n_st > 0) issue_stage(0, 0);
 
-    mbar_wait(lut_bar, 0);  // LUT resident
+    mbar_wait(lut_bar, (uint32_t)(seg & 1));  // LUT resident
 
     const uint32_t basereg = lut + (uint32_t)lane * 4u;
     const uint32_t plane = ring_w + (uint32_t)h * C::PLANE_RING_BYTES;
@@ -561,7 +575,6 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     };
 
     int Bg = 0, slot = 0, st = 0;
-    uint32_t phases = 0;  // bit s = parity to wait for on ring slot s
     auto next_stage = [&]() {
         const int next = (slot == C::RING_STAGES - 1) ? 0 : slot + 1;
         // the slot after the current one held stage st-2, which every lane group has left
@@ -697,6 +710,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
         const int qq = i / k, j = i - qq * k;
         out_keys[((long long)slice * q_stride_total + qg * QW + qq) * k + j] = lds64(lists + (uint32_t)(qq * KP + j) * 8u);
     }
+    __syncthreads();  // lists, LUT and scratch are free for the next segment
     if (STATS) {
         const unsigned long long t_e = now();
         auto wsum = [&](unsigned v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; };
@@ -719,6 +733,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
             }
         }
     }
+    }  // segment
 }
 
 // =============================================================================================
@@ -975,26 +990,46 @@ int launch_lut_build_scan(Ctx* ctx, int M, const float* q, long long nq, int D, 
 int scan_queries_per_cta(int M) { return M >= 4 ? 128 / M : 0; }
 
 // Work plan of the scan (see adc_scan_topk_kernel): n_full query groups get one whole-shard CTA each
-// (full waves of one-CTA-per-SM); the groups of the partial last wave are split into tail_s row slices.
-void scan_plan(int sm_count, long long qgroups, long long n_granules, int* n_full, int* tail_s) {
+// (full waves of one-CTA-per-SM); the (group, granule) work of the partial last wave is cut into
+// n_tail equal pieces, one per tail CTA, each piece = one or two segments.
+void scan_plan(int sm_count, long long qgroups, long long n_granules, ScanPlan* plan) {
     const long long waves = qgroups / sm_count;
     const long long rem = qgroups - waves * sm_count;
-    *n_full = (int)(waves * sm_count);
-    long long s = 1;
-    if (rem > 0) {
-        s = sm_count / rem;
-        const long long max_s = std::max<long long>(1, n_granules / 16);  // >= 1024 rows per slice
-        if (s > max_s) s = max_s;
-        if (s > 64) s = 64;
-        if (s < 1) s = 1;
+    plan->n_full = (int)(waves * sm_count);
+    plan->n_tail = 0;
+    plan->slices = 1;
+    plan->desc.clear();
+    if (rem == 0) return;
+    const long long work = rem * n_granules;
+    // one piece per SM, but no piece below 16 granules (1024 rows) and never fewer pieces than groups
+    const long long T = std::min<long long>(sm_count, std::max<long long>(rem, work / 16));
+    plan->n_tail = (int)T;
+    plan->desc.assign((size_t)T * 8, 0);
+    std::vector<int> next_slice((size_t)rem, 0);
+    for (long long t = 0; t < T; t++) {
+        int* d = plan->desc.data() + t * 8;
+        if (n_granules == 0 || T == rem) {  // one whole group per CTA (also the empty shard)
+            d[0] = (int)(plan->n_full + t); d[1] = 0; d[2] = 0; d[3] = (int)n_granules;
+            next_slice[t] = 1;
+            continue;
+        }
+        const long long lo = work * t / T, hi = work * (t + 1) / T;
+        const long long g1 = lo / n_granules;
+        d[0] = (int)(plan->n_full + g1); d[1] = next_slice[g1]++;
+        d[2] = (int)(lo - g1 * n_granules); d[3] = (int)(std::min(hi, (g1 + 1) * n_granules) - g1 * n_granules);
+        if (hi > (g1 + 1) * n_granules) {  // the piece runs on into the next group
+            const long long g2 = g1 + 1;
+            d[4] = (int)(plan->n_full + g2); d[5] = next_slice[g2]++;
+            d[6] = 0; d[7] = (int)(hi - g2 * n_granules);
+        }
     }
-    *tail_s = (int)s;
+    for (int v : next_slice) plan->slices = std::max(plan->slices, v);
 }
 
 template <int G, int WARPS_>
 static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
-                       int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys,
-                       float* warm_scratch) {
+                       int n_full, int n_tail, const int4* tail_desc, int k, float clamp, uint32_t id_base,
+                       unsigned long long* out_keys, float* warm_scratch) {
     using C = ScanCfg<G, WARPS_>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1002,7 +1037,7 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
         attr_set = true;
     }
     const long long n_gran = (n_rows + 63) / 64;
-    const unsigned grid = (unsigned)(n_full + (qgroups - n_full) * tail_s);
+    const unsigned grid = (unsigned)(n_full + n_tail);
     int soft = C::SOFT;
     if (const char* e = getenv("B200NN_SOFT")) soft = std::max(1, std::min(C::SB - 4, atoi(e)));
     if (getenv("B200NN_SCAN_STATS")) {  // development aid: counters of the candidate path, printed per launch
@@ -1016,7 +1051,7 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
         B2_CUDA(cudaMalloc(&d_stats, sizeof(hs)));
         B2_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(hs), ctx->stream));
         adc_scan_topk_kernel<G, WARPS_, true><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
-            codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft,
+            codesT, lut_scan, n_rows, n_gran, n_full, tail_desc, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft,
             d_stats, ctx->d_err);
         B2_CUDA(cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1031,7 +1066,7 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
         return 0;
     }
     adc_scan_topk_kernel<G, WARPS_, false><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
-        codesT, lut_scan, n_rows, n_gran, n_full, tail_s, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft,
+        codesT, lut_scan, n_rows, n_gran, n_full, tail_desc, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft,
         nullptr, ctx->d_err);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
@@ -1039,27 +1074,29 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
 }
 
 // floats of warm-up scratch the scan needs for a given plan (per CTA: 32 lanes' worth of queries x WARPS x 128 rows)
-size_t scan_warm_scratch_floats(int M, long long qgroups, int n_full, int tail_s) {
-    const long long grid = n_full + (qgroups - n_full) * tail_s;
-    return (size_t)grid * (size_t)(128 / M) * 16 * 128;
+size_t scan_warm_scratch_floats(int M, int n_full, int n_tail) {
+    return (size_t)(n_full + n_tail) * (size_t)(128 / M) * 16 * 128;
 }
 
 template <int G>
 static int scan_dispatch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
-                         int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys,
-                         float* warm_scratch) {
-    return scan_launch<G, 16>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
+                         int n_full, int n_tail, const int4* tail_desc, int k, float clamp, uint32_t id_base,
+                         unsigned long long* out_keys, float* warm_scratch) {
+    return scan_launch<G, 16>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, n_tail, tail_desc, k, clamp, id_base, out_keys,
+                              warm_scratch);
 }
 
 int launch_adc_scan_topk(Ctx* ctx, int M, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
-                         int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys,
-                         float* warm_scratch) {
+                         int n_full, int n_tail, const int* tail_desc_dev, int k, float clamp, uint32_t id_base,
+                         unsigned long long* out_keys, float* warm_scratch) {
+    const int4* tail_desc = reinterpret_cast<const int4*>(tail_desc_dev);
+    if (n_tail > 0 && !tail_desc) B2_FAIL(-1, "adc_scan: tail CTAs without descriptors");
     if (k < 1 || k > KP) B2_FAIL(-4, "fused ADC top-k supports 1 <= k <= 128");
     switch (M) {
-        case 4: return scan_dispatch<1>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
-        case 8: return scan_dispatch<2>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
-        case 16: return scan_dispatch<4>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
-        case 32: return scan_dispatch<8>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, tail_s, k, clamp, id_base, out_keys, warm_scratch);
+        case 4: return scan_dispatch<1>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, n_tail, tail_desc, k, clamp, id_base, out_keys, warm_scratch);
+        case 8: return scan_dispatch<2>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, n_tail, tail_desc, k, clamp, id_base, out_keys, warm_scratch);
+        case 16: return scan_dispatch<4>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, n_tail, tail_desc, k, clamp, id_base, out_keys, warm_scratch);
+        case 32: return scan_dispatch<8>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, n_tail, tail_desc, k, clamp, id_base, out_keys, warm_scratch);
         default: B2_FAIL(-4, "fast ADC scan supports M in {4, 8, 16, 32}");
     }
 }

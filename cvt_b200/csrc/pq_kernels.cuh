@@ -1,5 +1,7 @@
 // pq_kernels.cuh -- launchers of the (O)PQ kernels (definitions in pq_kernels.cu).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace b200nn {
@@ -15,12 +17,18 @@ int launch_lut_build_std(Ctx* ctx, const float* q, long long nq, int D, const in
 int launch_lut_build_scan(Ctx* ctx, int M, const float* q, long long nq, int D, const float* centroid, const float* cb,
                           float* lut_scan);
 int scan_queries_per_cta(int M);
-void scan_plan(int sm_count, long long qgroups, long long n_granules, int* n_full, int* tail_s);
-// out_keys: [max(1,tail_s)][qgroups*QW][k]; must be pre-filled with 0xFF bytes when tail_s > 1
-size_t scan_warm_scratch_floats(int M, long long qgroups, int n_full, int tail_s);
+// Work plan of the fused scan: n_full whole-shard CTAs + n_tail tail CTAs; desc = 8 ints per tail CTA
+// (two {query group, output slice, granule lo, granule hi} segments); slices = output lists per query.
+struct ScanPlan {
+    int n_full = 0, n_tail = 0, slices = 1;
+    std::vector<int> desc;
+};
+void scan_plan(int sm_count, long long qgroups, long long n_granules, ScanPlan* plan);
+// out_keys: [plan.slices][qgroups*QW][k]; must be pre-filled with 0xFF bytes when plan.slices > 1
+size_t scan_warm_scratch_floats(int M, int n_full, int n_tail);
 int launch_adc_scan_topk(Ctx* ctx, int M, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
-                         int n_full, int tail_s, int k, float clamp, uint32_t id_base, unsigned long long* out_keys,
-                         float* warm_scratch /* scan_warm_scratch_floats() floats */);
+                         int n_full, int n_tail, const int* tail_desc_dev /* plan.desc on the device */, int k, float clamp,
+                         uint32_t id_base, unsigned long long* out_keys, float* warm_scratch /* scan_warm_scratch_floats() floats */);
 int launch_fill_f32(Ctx* ctx, float* p, long long n, float v);
 int launch_ivf_scan(Ctx* ctx, const float* lut, const int* probes, const long long* list_off, const unsigned char* codes_sorted,
                     const int* slot_sorted, int M, int ksub, long long nq, int nprobe, long long out_stride, float* out);

@@ -86,7 +86,8 @@ __device__ __forceinline__ float tau_f32_of(unsigned long long tkey) {
     return tkey == KEY_MAX ? __int_as_float(0x7f800000) : f32_from_orderable((uint32_t)(tkey >> 32));
 }
 
-// Merge of L sorted key lists per query (defined in topk_merge.cu).  keys[l*list_stride + q*k + j].
+// Merge of L sorted key lists per query (defined in topk_merge.cu).  keys[chunk][l][list_stride/k][k],
+// chunk = q / (list_stride/k); a single chunk is keys[l*list_stride + q*k + j].
 int launch_topk_merge(Ctx* ctx, const unsigned long long* keys, int L, long long nq, int k, long long list_stride,
                       float* out_dist_f, int* out_dist_i, unsigned long long* out_id, unsigned long long* out_key);
 

@@ -6,8 +6,10 @@ namespace b200nn {
 // ---------------------------------------------------------------------------------------------
 // Merge of L sorted key lists per query (slices of one GPU, or the all-gathered shard results).
 // One warp per query; rank = own index + sum over the other lists of lower_bound(key).
-// keys[(l * list_stride) + q * k + j].  Missing results (fewer than k real records) are written
-// as (+inf | INT32_MAX, UINT64_MAX).
+// Layout: keys[chunk][l][cq][k] with cq = list_stride / k queries per chunk; query q lives in chunk
+// q / cq.  One chunk (q < cq) is the plain [L][cq][k] layout of slices / row shards; several chunks
+// are the all-gathered records of a (query chunk x row shard) grid of ranks.  Missing results (fewer
+// than k real records) are written as (+inf | INT32_MAX, UINT64_MAX).
 // ---------------------------------------------------------------------------------------------
 __global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, int L, long long nq, int k,
                                   long long list_stride, float* __restrict__ out_dist_f, int* __restrict__ out_dist_i,
@@ -17,7 +19,8 @@ __global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, i
     const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + w;
     if (q >= nq) return;
     unsigned long long* sk = s_keys + (size_t)w * L * k;
-    const unsigned long long* base = keys + q * k;
+    const long long cq = list_stride / k, chunk = q / cq;
+    const unsigned long long* base = keys + (chunk * (L - 1) * cq + q) * k;  // = ((chunk*L)*cq + (q - chunk*cq)) * k
     for (int e = lane; e < L * k; e += 32) {
         const int l = e / k, j = e - l * k;
         sk[e] = base[(long long)l * list_stride + j];

@@ -1,7 +1,9 @@
-"""Row-sharded (O)PQ search across the GPUs of one box: one process per GPU (torch.distributed /
-NCCL for the plumbing), each rank owns a contiguous block of database rows as its own index,
-queries are replicated, and the only exchange is ONE all-gather of the per-shard top-k records
-(64-bit sortable keys) followed by a per-query merge kernel.
+"""Sharded (O)PQ search across the GPUs of one box: one process per GPU (torch.distributed / NCCL
+for the plumbing).  The ranks form a (query chunk x row shard) grid: a rank owns a contiguous block
+of database rows as its own index and serves one chunk of the query batch; the only exchange is ONE
+all-gather of the per-rank top-k records (64-bit sortable keys) followed by a
+per-query merge kernel over the row shards.  row_shards = world is the plain row-sharded layout
+(queries replicated); plan_layout() chooses the grid.
 
 The merge order is the reference's (score, id) lexicographic order on GLOBAL ids, so the sharded
 result is identical to a single-index search.  (The same shape as the unbuilt boost.MPI
@@ -48,147 +50,148 @@ def merge_keys_host(keys_all: np.ndarray, k: int) -> np.ndarray:
     return np.sort(flat, axis=1)[:, :k]
 
 
-def wave_split(nq: int, queries_per_cta: int, sm_count: int) -> list[tuple[int, int]]:
-    """Query chunks for the overlapped exchange: the scan runs one CTA per group of `queries_per_cta`
-    queries and one CTA per SM, so the first chunk is the whole waves of the batch and the second the
-    partial last wave (which the scan splits into row slices).  While the second chunk is scanned, the
-    first chunk's top-k records are already being gathered and merged.  One chunk when the batch has
-    no whole wave or no remainder."""
-    groups = -(-nq // queries_per_cta)
-    first = (groups // sm_count) * sm_count * queries_per_cta
-    if first <= 0 or first >= nq:
-        return [(0, nq)]
-    return [(0, first), (first, nq)]
+def merge_grid_host(keys_grid: np.ndarray, nq: int, k: int) -> np.ndarray:
+    """[Q, R, chunk_q, k] gathered records of a (query chunk x row shard) grid -> [nq, k]: the CPU twin of
+    b200nn_topk_merge_grid_dev (rows past nq are padding)."""
+    Q, R, cq, _ = keys_grid.shape
+    return np.concatenate([merge_keys_host(keys_grid[c], k) for c in range(Q)], axis=0)[:nq]
+
+
+# ---- layout: how the ranks of one box split (rows x queries) -----------------------------------
+# Constants of the cost model, measured on B200 this round (profiles/r01_summary.md, DESIGN.md section 5):
+_SCAN_BYTES_PER_S = 6.0e12    # algorithmic code bytes per second of the streaming phase of the fused scan, one GPU
+_WARMUP_S = 30e-6             # parked warm-up + selection (phases A + B) per (CTA, segment)
+_CANDIDATE_S = 0.015e-6       # streamed candidate, per (query, segment): ~1.5 k ln(rows/2048) of them
+_LUT_S_PER_QUERY = 0.02e-6    # rotate + LUT build per query
+_EXCHANGE_S = 40e-6           # all-gather launch + rank skew floor
+_LINK_BYTES_PER_S = 300e9     # effective all-gather bandwidth at these message sizes
+_MERGE_BYTES_PER_S = 1.0e12   # merge kernel: bytes of gathered records it reads
+
+
+def layout_cost(world: int, row_shards: int, n_rows: int, batch: int, M: int, k: int, sm_count: int = 148) -> float:
+    """Modelled seconds per step of a (row_shards x world/row_shards) grid of ranks."""
+    R, Q = row_shards, world // row_shards
+    rows = -(-n_rows // R)
+    bq = -(-batch // Q)
+    qw = max(1, 128 // M)
+    groups = -(-bq // qw)
+
+    def segment(r):  # top-k warm-up of one (CTA, segment) over r rows
+        return _WARMUP_S + qw * 1.5 * k * float(np.log(max(r, 4096.0) / 2048.0)) * _CANDIDATE_S
+
+    waves, rem = divmod(groups, sm_count)
+    # every SM runs `waves` whole-shard segments, then a piece of the last wave (1-2 segments, 1.5 on average)
+    t_warm = waves * segment(rows) + (1.5 * segment(rem * rows / sm_count) if rem else 0.0)
+    t_scan = bq * rows * M / _SCAN_BYTES_PER_S
+    t_lut = bq * _LUT_S_PER_QUERY
+    gathered = world * bq * k * 8
+    t_x = 0.0 if world == 1 else _EXCHANGE_S + gathered / _LINK_BYTES_PER_S + (gathered / _MERGE_BYTES_PER_S if R > 1 else 0.0)
+    return t_scan + t_warm + t_lut + t_x
+
+
+def plan_layout(world: int, n_rows: int, batch: int, M: int, k: int, sm_count: int = 148,
+                max_rows_per_gpu: int = 1 << 30, tolerance: float = 0.02) -> tuple[int, int]:
+    """(row_shards R, query_chunks Q) with R * Q = world.
+
+    R = world is the memory-minimal layout (every rank scans its block of rows for
+    the whole batch).  It is kept whenever the model puts it within `tolerance` of the best layout; for a
+    database so small that a 1/world shard no longer amortises the per-(query, CTA) top-k warm-up (cfg3:
+    1M rows = 16 MB of codes), ranks instead replicate row blocks and split the query batch, which cuts
+    the warm-ups, the LUT builds and the gathered payload by Q.  The collective is the same single
+    all-gather either way."""
+    cands = [r for r in range(1, world + 1) if world % r == 0 and -(-n_rows // r) <= max_rows_per_gpu]
+    if not cands:
+        return world, 1
+    cost = {r: layout_cost(world, r, n_rows, batch, M, k, sm_count) for r in cands}
+    best = min(cost.values())
+    r = max(r for r in cands if cost[r] <= best * (1.0 + tolerance))
+    return r, world // r
+
+
+def grid_coords(rank: int, row_shards: int) -> tuple[int, int]:
+    """rank -> (row shard r, query chunk c); rank = c * row_shards + r (row shards of one chunk are adjacent
+    ranks, so the gathered buffer reads [Q][R][chunk_q][k])."""
+    return rank % row_shards, rank // row_shards
+
+
+def query_chunk(nq: int, n_chunks: int, c: int) -> tuple[int, int, int]:
+    """Queries [lo, hi) of chunk c and the (padded) chunk size."""
+    cq = -(-nq // n_chunks) if nq else 0
+    lo = min(nq, c * cq)
+    return lo, min(nq, lo + cq), cq
 
 
 class ShardedPQ:
-    """Distributed search over per-rank PQIndex shards.
+    """Distributed search over a (query chunk x row shard) grid of ranks, one PQIndex shard per rank.
 
-    `local_search(q, k) -> keys [nq, k] (uint64 tensor, ascending)` and `merge(keys_all [L,nq,k]) ->
-    (dist, ids)` are injectable so that the exchange logic runs under gloo on CPU in the tests;
-    on GPUs they are the C-ABI calls (pq_search_dev with out_key, topk_merge_dev).
+    `local_search(q_chunk, k) -> keys [n, k]` (int64 view of the uint64 records, ascending, GLOBAL ids)
+    and `merge(keys_grid [Q, R, chunk_q, k], nq) -> (dist, ids)` are injectable so that the exchange
+    logic runs under gloo on CPU in the tests; on GPUs they are the C-ABI calls (pq_search_dev with
+    out_key, topk_merge_grid_dev).  The collective is ONE all-gather of [chunk_q, k] records per rank."""
 
-    The collective stays ONE all-gather of [nq, k] records per rank; with `split` it is issued in
-    query chunks (same total payload) so that a chunk's gather + merge runs on `side` (a second
-    stream) underneath the scan of the next chunk.  Chunked calls pass rows=(lo, hi, nq) to both
-    callbacks; `assemble(parts)` turns the per-chunk results into the [nq, k] result."""
-
-    def __init__(self, dist_module, rank: int, world: int, local_search, merge, split=None, side=None, assemble=None):
+    def __init__(self, dist_module, rank: int, world: int, local_search, merge, row_shards: int | None = None):
         self.dist, self.rank, self.world = dist_module, rank, world
+        self.R = world if row_shards is None else int(row_shards)
+        if self.R < 1 or world % self.R:
+            raise ValueError(f"row_shards={row_shards} must divide world={world}")
+        self.Q = world // self.R
+        self.r, self.c = grid_coords(rank, self.R)
         self.local_search, self.merge = local_search, merge
-        self.split, self.side, self.assemble = split, side, assemble
         self._gathered = {}
 
-    def _exchange(self, keys_local, **rows):
+    def search(self, q, k: int):
         import torch
-        nq, kk = keys_local.shape
-        tag = (rows.get("rows", (0,))[0], nq, kk)
+        nq = q.shape[0]
+        lo, hi, cq = query_chunk(nq, self.Q, self.c)
+        keys = self.local_search(q[lo:hi], k)
+        if self.world == 1:
+            return self.merge(keys.view(1, 1, nq, k), nq)
+        if keys.shape[0] != cq:  # ragged last chunk: pad with empty records (all-gather needs equal parts)
+            pad = torch.full((cq, k), -1, dtype=keys.dtype, device=keys.device)
+            pad[: hi - lo] = keys
+            keys = pad
+        tag = (cq, k, keys.device)
         gathered = self._gathered.get(tag)
         if gathered is None:
-            gathered = self._gathered[tag] = torch.empty((self.world * nq, kk), dtype=keys_local.dtype, device=keys_local.device)
-        self.dist.all_gather_into_tensor(gathered, keys_local)  # the single collective of the path
-        return self.merge(gathered.view(self.world, nq, kk), **rows)
-
-    def search(self, q, k: int):
-        nq = q.shape[0]
-        if self.world == 1:
-            return self.merge(self.local_search(q, k).unsqueeze(0))  # [nq, k] int64 view of uint64 keys
-        chunks = self.split(nq) if self.split is not None else [(0, nq)]
-        if len(chunks) == 1:
-            return self._exchange(self.local_search(q, k))
-        parts = [None] * len(chunks)
-        for ci, (lo, hi) in enumerate(chunks):
-            rows = (lo, hi, nq)
-            keys_c = self.local_search(q[lo:hi], k, rows=rows)
-
-            def exchange(ci=ci, keys_c=keys_c, rows=rows):
-                parts[ci] = self._exchange(keys_c, rows=rows)
-
-            if self.side is not None:
-                self.side.run(exchange)  # after everything queued so far; the caller's stream goes on with the next chunk
-            else:
-                exchange()
-        if self.side is not None:
-            self.side.join()
-        if self.assemble is not None:
-            return self.assemble(parts)
-        import torch
-        return tuple(torch.cat([torch.as_tensor(p[j]) for p in parts]) for j in range(2))
+            gathered = self._gathered[tag] = torch.empty((self.world * cq, k), dtype=keys.dtype, device=keys.device)
+        self.dist.all_gather_into_tensor(gathered, keys)  # the single collective of the path
+        return self.merge(gathered.view(self.Q, self.R, cq, k), nq)
 
 
-class _SideStream:
-    """Runs the exchange of a finished chunk on a second CUDA stream (torch + the library's context)."""
+def make_gpu_sharded(ctx, index, dist_module, rank: int, world: int, id_base: int, nprobe: int = 1,
+                     row_shards: int | None = None):
+    """Wire a ShardedPQ to the CUDA library for torch CUDA tensors.  `index` holds the rows of row shard
+    rank % row_shards (first global row = id_base).  The caller's current torch stream must be the stream
+    the context launches on (ctx.set_stream).
 
-    def __init__(self, ctx, device):
-        import torch
-        self.torch, self.ctx = torch, ctx
-        self.stream = torch.cuda.Stream(device=device)
-        self.ev = torch.cuda.Event()
-
-    def run(self, fn):
-        torch = self.torch
-        cur = torch.cuda.current_stream()
-        if cur.cuda_stream == 0:
-            raise RuntimeError("overlapped exchange needs a non-default current stream shared with the context (ctx.set_stream)")
-        self.ev.record(cur)
-        self.stream.wait_event(self.ev)
-        self.ctx.set_stream(self.stream.cuda_stream)
-        try:
-            with torch.cuda.stream(self.stream):
-                fn()
-        finally:
-            self.ctx.set_stream(cur.cuda_stream)
-
-    def join(self):
-        self.torch.cuda.current_stream().wait_stream(self.stream)
-
-
-def make_gpu_sharded(ctx, index, dist_module, rank: int, world: int, id_base: int, nprobe: int = 1, overlap: bool = False):
-    """Wire a ShardedPQ to the CUDA library for torch CUDA tensors.  The caller's current torch stream
-    must be the stream the context launches on (ctx.set_stream).
-
-    overlap=True issues the exchange in wave-aligned query chunks on a side stream.  Measured on 2 B200s
-    (cfg3, 500 k rows per GPU): 6.39 ms/step against 6.18 ms for the plain single gather -- the scan's own
-    plan back-fills the SMs of the partial last wave with row slices of the tail groups inside ONE grid,
-    and cutting the batch into two launches exposes the first launch's wave tail; the gather + merge it
-    hides cost only ~0.05 ms there.  Hence off by default."""
+    (An exchange issued in wave-aligned query chunks on a side stream, overlapping the next chunk's scan,
+    was built and measured earlier this round: 6.39 vs 6.18 ms per step on 2 B200s -- slower, because two
+    scan launches expose the first launch's wave tail -- and removed.)"""
     import torch
 
-    bufs = {}
+    local_bufs, merged_bufs, state = {}, {}, {}  # reused across steps: no allocator traffic inside the timed region
 
-    def _buffers(nq, k, device):
-        key = (nq, k)
-        if key not in bufs:  # reused across steps: no allocator traffic inside the timed region
-            bufs[key] = dict(keys=torch.empty((nq, k), dtype=torch.int64, device=device),
-                             dist=torch.empty((nq, k), dtype=torch.float32, device=device),
-                             ids=torch.empty((nq, k), dtype=torch.int64, device=device),
-                             mdist=torch.empty((nq, k), dtype=torch.float32, device=device),
-                             mids=torch.empty((nq, k), dtype=torch.int64, device=device))
-        return bufs[key]
+    def local_search(q, k):
+        n = q.shape[0]
+        if (n, k) not in local_bufs:
+            local_bufs[(n, k)] = (torch.full((max(n, 1), k), -1, dtype=torch.int64, device=q.device),
+                                  torch.empty((max(n, 1), k), dtype=torch.float32, device=q.device),
+                                  torch.empty((max(n, 1), k), dtype=torch.int64, device=q.device))
+        keys, dist, ids = local_bufs[(n, k)]
+        if n:
+            index.search_dev(q.data_ptr(), n, k, nprobe, dist.data_ptr(), ids.data_ptr(), keys.data_ptr(), id_base)
+        state["local"] = (dist[:n], ids[:n])
+        return keys[:n]
 
-    def local_search(q, k, rows=None):
-        lo, hi, nq = rows if rows is not None else (0, q.shape[0], q.shape[0])
-        b = _buffers(nq, k, q.device)
-        keys, dist, ids = b["keys"][lo:hi], b["dist"][lo:hi], b["ids"][lo:hi]
-        index.search_dev(q.data_ptr(), hi - lo, k, nprobe, dist.data_ptr(), ids.data_ptr(), keys.data_ptr(), id_base)
-        local_search.last = (b["dist"], b["ids"])
-        return keys
-
-    def merge(keys_all, rows=None):
-        L, nq_c, k = keys_all.shape
-        if L == 1 and hasattr(local_search, "last"):
-            return local_search.last
-        lo, hi, nq = rows if rows is not None else (0, nq_c, nq_c)
-        b = _buffers(nq, k, keys_all.device)
-        dist, ids = b["mdist"], b["mids"]
-        ctx.topk_merge_dev(keys_all.data_ptr(), L, nq_c, k, dist[lo:hi].data_ptr(), ids[lo:hi].data_ptr())
+    def merge(keys_grid, nq):
+        Q, R, cq, k = keys_grid.shape
+        if Q * R == 1:
+            return state["local"]
+        if (nq, k) not in merged_bufs:
+            merged_bufs[(nq, k)] = (torch.empty((nq, k), dtype=torch.float32, device=keys_grid.device),
+                                    torch.empty((nq, k), dtype=torch.int64, device=keys_grid.device))
+        dist, ids = merged_bufs[(nq, k)]
+        ctx.topk_merge_grid_dev(keys_grid.data_ptr(), Q, R, cq, nq, k, dist.data_ptr(), ids.data_ptr())
         return dist, ids
 
-    split = side = None
-    # the fused flat scan (K = 1, 256 centroids, M in {4, 8, 16, 32}) runs 128/M queries per CTA, one CTA per SM
-    if overlap and world > 1 and nprobe == 1 and index.K == 1 and index.ksub == 256 and index.M in (4, 8, 16, 32):
-        dev = torch.device("cuda", torch.cuda.current_device())
-        qpc, sms = 128 // index.M, torch.cuda.get_device_properties(dev).multi_processor_count
-        split = lambda nq: wave_split(nq, qpc, sms)
-        side = _SideStream(ctx, dev)
-    return ShardedPQ(dist_module, rank, world, local_search, merge, split=split, side=side, assemble=lambda parts: parts[-1])
+    return ShardedPQ(dist_module, rank, world, local_search, merge, row_shards=row_shards)

@@ -117,6 +117,15 @@ int b200nn_pq_search_dev(b200nn_pq_t idx, const float* q_raw_dev, size_t nq, int
 /* merge L sorted key lists per query ([L][nq][k] u64, e.g. the all-gathered shard results). */
 int b200nn_topk_merge_dev(b200nn_ctx_t ctx, const uint64_t* keys_dev, int L, size_t nq, size_t k, float* out_dist_dev,
                           uint64_t* out_id_dev);
+/* the same merge over the all-gathered records of a (query chunk x row shard) grid of ranks:
+ * keys [n_chunks][L][chunk_q][k], rank = chunk * L + shard; batch query q = row q % chunk_q of chunk q / chunk_q. */
+int b200nn_topk_merge_grid_dev(b200nn_ctx_t ctx, const uint64_t* keys_dev, int n_chunks, int L, size_t chunk_q, size_t nq,
+                               size_t k, float* out_dist_dev, uint64_t* out_id_dev);
+/* host-only: the work plan of the fused flat scan for nq queries x n_rows rows on sm_count SMs -- n_full
+ * whole-shard CTAs, n_tail tail CTAs whose equal pieces of the last wave are described by 8 ints each
+ * (two {query group, output slice, granule lo, granule hi} segments; granule = 64 rows), slices = lists per query. */
+int b200nn_pq_scan_plan(int sm_count, int M, size_t nq, size_t n_rows, int* n_full, int* n_tail, int* slices, int32_t* desc,
+                        size_t desc_capacity);
 int b200nn_pq_save_index(b200nn_pq_t idx, const char* dir_or_path, const char* const* group_paths); /* App. A-3 */
 int b200nn_pq_load_index(b200nn_ctx_t ctx, const char* path, const int32_t* perm, float clamp, b200nn_pq_t* out);
 /* timing of the last pq_search[_dev] stages in ms: [rotate, lut, scan, merge] (CUDA events). */

@@ -59,3 +59,41 @@ def test_product_does_not_touch_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                     txt = open(os.path.join(dp, f), errors="ignore").read()
                     assert "oracle" not in txt.lower() or f == "quick_scan_bench.py", f"{dp}/{f} mentions the oracle"
+
+
+@pytest.mark.parametrize("M", [4, 8, 16, 32])
+def test_scan_plan_tiles_the_work_exactly(lib, M):
+    """Host-only: the fused scan's work plan (whole-shard CTAs + equal pieces of the last wave) covers every
+    (query group, granule) exactly once, numbers a group's output slices 0..c-1 and balances the tail."""
+    import numpy as np
+    from cvt_b200 import capi
+    qw = 128 // M
+    for sm in (148, 132, 7):
+        for nq, n_rows in [(4096, 1_000_000), (512, 1_000_000), (1024, 500_000), (4096, 125_000), (7, 100), (100, 0),
+                           (sm * qw, 20_000), (sm * qw + 1, 20_000), (5000, 53), (801, 20_000), (3, 1_000_003)]:
+            n_full, n_tail, slices, desc = capi.scan_plan(sm, M, nq, n_rows)
+            groups, gran = -(-nq // qw), -(-n_rows // 64)
+            assert n_full == (groups // sm) * sm and n_full + (1 if n_tail else 0) * 1 <= groups + n_tail
+            rem = groups - n_full
+            assert (n_tail == 0) == (rem == 0) and n_tail <= sm and (rem == 0 or n_tail >= rem)
+            cover = {g: [] for g in range(n_full, groups)}
+            sizes = []
+            for t in range(n_tail):
+                size = 0
+                for s in range(2):
+                    g, sl, lo, hi = (int(v) for v in desc[t, s])
+                    if s == 1 and lo >= hi:
+                        continue
+                    assert n_full <= g < groups and 0 <= lo <= hi <= gran and 0 <= sl < slices
+                    cover[g].append((sl, lo, hi))
+                    size += hi - lo
+                sizes.append(size)
+            for g, segs in cover.items():
+                segs.sort()
+                assert [s[0] for s in segs] == list(range(len(segs))), "slices of a group are numbered 0..c-1"
+                assert segs[0][1] == 0 and segs[-1][2] == gran and all(a[2] == b[1] for a, b in zip(segs, segs[1:]))
+            if n_tail:
+                assert max(sizes) - min(sizes) <= 1, "tail pieces are equal to within one granule"
+                assert slices == max(len(v) for v in cover.values())
+            else:
+                assert slices == 1

@@ -92,6 +92,25 @@ def test_cfg3_full_size_properties(ctx, cfg3):
     ctx.topk_merge_dev(gathered.data_ptr(), G, c["B"], 100, dm.data_ptr(), im.data_ptr())
     ctx.synchronize()
     assert torch.equal(im, i100) and torch.equal(dm, d100)
+    # (query chunk x row shard) grids of ranks: 2 row shards x 4 query chunks, and 1 x 8 (rows replicated)
+    for R, Q in ((2, 4), (1, 8)):
+        cq = c["B"] // Q
+        grid = torch.empty((Q, R, cq, 100), dtype=torch.int64, device="cuda")
+        for r in range(R):
+            lo, hi = sharded.shard_bounds(c["n"], R, r)
+            sh = idx if R == 1 else capi.PQIndex.create(ctx, c["coarse"], c["cb"], perm=c["perm"], clamp=1.0)
+            if R > 1:
+                sh.add(c["db"][lo:hi])
+            for ch in range(Q):
+                qlo, qhi, cq2 = sharded.query_chunk(c["B"], Q, ch)
+                assert cq2 == cq
+                _, _, keys = _search_dev(ctx, sh, q_t[qlo:qhi], 100, id_base=lo)
+                grid[ch, r] = keys
+            if R > 1:
+                sh.close()
+        ctx.topk_merge_grid_dev(grid.data_ptr(), Q, R, cq, c["B"], 100, dm.data_ptr(), im.data_ptr())
+        ctx.synchronize()
+        assert torch.equal(im, i100) and torch.equal(dm, d100), (R, Q)
     idx.close()
 
 

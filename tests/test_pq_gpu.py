@@ -151,6 +151,28 @@ def test_fast_scan_vs_oracle_and_generic(ctx, M, n, nq, k):
     idx.close()
 
 
+@pytest.mark.parametrize("M,n,nq,k", [(16, 20_000, 801, 100), (16, 20_000, 1424, 10), (32, 12_000, 700, 100), (8, 9_000, 2500, 16),
+                                       (4, 6_000, 5000, 5)])
+def test_fast_scan_tail_pieces_straddle_query_groups(ctx, M, n, nq, k):
+    """Batches whose last wave is cut into equal pieces that straddle query-group boundaries (a tail CTA
+    then runs two segments: two LUTs, two top-k lists, two output slices) == the oracle, every query."""
+    from cvt_b200 import capi
+    D = 128
+    n_full, n_tail, slices, desc = capi.scan_plan(148, M, nq, n)
+    assert n_tail > 0 and np.any(desc[:, 1, 3] > desc[:, 1, 2]), "the case must contain two-segment CTAs"
+    idx, db, perm, coarse, cb = _random_flat_index(ctx, n, D, M, seed=2000 + M + n, clamp=1.0)
+    q = synth.sift_like(nq, D, seed=99 + M)
+    Dg, Ig = idx.search(q, k=k, nprobe=1)
+    _, _, codes = idx.get_rows()
+    od, oi = orc.opq_search_flat(orc.opq_reorder(q, perm), coarse[0], cb, codes, k, clamp=1.0)
+    assert np.array_equal(Ig.astype(np.int64), oi)
+    assert np.array_equal(_bits(Dg), _bits(od))
+    # and again with a different batch size on the same index (the cached plan must follow the shape)
+    D2, I2 = idx.search(q[: nq // 3], k=k, nprobe=1)
+    assert np.array_equal(I2.astype(np.int64), oi[: nq // 3]) and np.array_equal(_bits(D2), _bits(od[: nq // 3]))
+    idx.close()
+
+
 def test_clamp_ties_fast_scan(ctx):
     """threhold = 1.0 (IVFOPQ.cpp:5): scores >= 1 collapse to exactly 1.0 and ids break the ties."""
     n, D, M, k = 3000, 128, 16, 64
