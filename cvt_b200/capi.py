@@ -23,7 +23,7 @@ SYMBOLS = [
     "b200nn_flat_search", "b200nn_flat_search_dev", "b200nn_flat_save", "b200nn_flat_load",
     "b200nn_pq_create", "b200nn_pq_load_model", "b200nn_pq_destroy", "b200nn_pq_set_clamp", "b200nn_pq_info",
     "b200nn_pq_rotate", "b200nn_pq_encode", "b200nn_pq_add", "b200nn_pq_add_dev", "b200nn_pq_add_rotated", "b200nn_pq_get_rows",
-    "b200nn_pq_build_lut", "b200nn_pq_scores", "b200nn_pq_search", "b200nn_pq_search_dev", "b200nn_topk_merge_dev",
+    "b200nn_pq_build_lut", "b200nn_pq_scores", "b200nn_pq_query_groups", "b200nn_pq_search", "b200nn_pq_search_dev", "b200nn_topk_merge_dev",
     "b200nn_topk_merge_grid_dev", "b200nn_pq_scan_plan",
     "b200nn_pq_save_index", "b200nn_pq_load_index", "b200nn_pq_last_timing", "b200nn_pq_scan_bytes",
     "b200nn_sq_create", "b200nn_sq_destroy", "b200nn_sq_train_minmax", "b200nn_sq_encode", "b200nn_sq_decode",
@@ -243,6 +243,17 @@ class PQIndex:
         out = np.empty((q_raw.shape[0], self.n_groups), dtype=np.float32)
         _check(load().b200nn_pq_scores(self.h, _vp(q_raw), C.c_size_t(q_raw.shape[0]), C.c_int(nprobe), _vp(out)), "pq_scores")
         return out
+
+    def query_groups(self, q_raw, frame_off, k, nprobe=3):
+        """Multi-frame query videos -> the k best indexed videos each (multi_frame_index_test.cpp:54-68)."""
+        q_raw = _f32(q_raw)
+        off = np.ascontiguousarray(frame_off, dtype=np.int64)
+        nv = off.shape[0] - 1
+        S = np.empty((nv, k), dtype=np.float32)
+        G = np.empty((nv, k), dtype=np.uint64)
+        _check(load().b200nn_pq_query_groups(self.h, _vp(q_raw), _vp(off), C.c_size_t(nv), C.c_int(nprobe), C.c_size_t(k), _vp(S), _vp(G)),
+               "pq_query_groups")
+        return S, G
 
     def search(self, q_raw, k, nprobe=1):
         q_raw = _f32(q_raw)

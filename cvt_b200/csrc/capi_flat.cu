@@ -29,7 +29,8 @@ struct b200nn_flat {
     // tensor-core scan layout of u8 rows (metric 2): canonical 256-row tiles + |x|^2
     long long tc_rows = -1;
     DevBuf<unsigned char> xcan;
-    DevBuf<int> xnorm;
+    DevBuf<int> xnorm;   // per-tile row meta: |x|^2 and label rank
+    DevBuf<int> ws_thr;  // per-query shared distance bound of the tensor-core scan
     DevBuf<unsigned char> ws_q;
     DevBuf<unsigned long long> ws_keys, ws_id;
     DevBuf<float> ws_dist;
@@ -95,16 +96,16 @@ int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, vo
         // u8 x u8 -> s32 contraction on the tensor cores (tcgen05 kind::i8) with the fused top-k epilogue
         if (p->tc_rows != (long long)p->n) {
             const long long n_pad = std::max<long long>(256, ((long long)p->n + 255) / 256 * 256);
-            if ((rc = p->xcan.ensure((size_t)n_pad * p->dim)) || (rc = p->xnorm.ensure((size_t)n_pad))) return rc;
-            if ((rc = launch_u8_rows_to_canonical(c, p->data.p, (long long)p->n, (int)p->dim, p->xcan.p, p->xnorm.p, n_pad))) return rc;
+            if ((rc = p->xcan.ensure((size_t)n_pad * p->dim)) || (rc = p->xnorm.ensure((size_t)n_pad * 2))) return rc;
+            if ((rc = launch_u8_rows_to_canonical(c, p->data.p, p->rank.p, (long long)p->n, (int)p->dim, p->xcan.p, p->xnorm.p, n_pad))) return rc;
             p->tc_rows = (long long)p->n;
         }
-        const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, (long long)p->n);
-        if ((rc = p->ws_keys.ensure((size_t)S * nq * k))) return rc;
-        if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, p->rank.p, (long long)p->n, (int)p->dim, (const unsigned char*)q_dev,
-                                    (long long)nq, S, (int)k, p->ws_keys.p)))
+        const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, (long long)p->n), L = S * u8_scan_tc_lists_per_slice();
+        if ((rc = p->ws_keys.ensure((size_t)L * nq * k)) || (rc = p->ws_thr.ensure(nq))) return rc;
+        if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, (long long)p->n, (int)p->dim, (const unsigned char*)q_dev, (long long)nq, S,
+                                    (int)k, p->ws_thr.p, p->ws_keys.p)))
             return rc;
-        if ((rc = launch_topk_merge(c, p->ws_keys.p, S, (long long)nq, (int)k, (long long)(nq * k), nullptr, (int*)out_dist, out_label, nullptr)))
+        if ((rc = launch_topk_merge(c, p->ws_keys.p, L, (long long)nq, (int)k, (long long)(nq * k), nullptr, (int*)out_dist, out_label, nullptr)))
             return rc;
         return launch_rank_to_label(c, out_label, (long long)(nq * k), p->label_sorted.p);
     }

@@ -502,6 +502,61 @@ int b200nn_pq_scores(b200nn_pq_t p, const float* q_raw, size_t nq, int nprobe, f
     return 0;
 }
 
+// f-5: what the reference's query main does with Query's output (multi_frame_index_test.cpp:54-68): the frames
+// of one query video are scored against every indexed video (QueryThrehold: clamp-initialised, min per videoId),
+// the per-frame scores are summed per video and get_sort_results keeps the k smallest (score, videoId).
+// Everything stays on the device; only [n_videos, k] results come back.
+int b200nn_pq_query_groups(b200nn_pq_t p, const float* q_raw, const int64_t* frame_off, size_t n_videos, int nprobe, size_t k,
+                           float* out_score, uint64_t* out_group) {
+    if (!p || !frame_off || (n_videos && (!out_score || !out_group))) B2_FAIL(B200NN_ERR_INVALID, "pq_query_groups: NULL argument");
+    if (nprobe < 1 || nprobe > p->K) B2_FAIL(B200NN_ERR_INVALID, "pq_query_groups: nprobe must be in [1, K]");
+    if (k < 1 || k > (size_t)KP) B2_FAIL(B200NN_ERR_UNSUPPORTED, "pq_query_groups: k must be in [1, 128]");
+    for (size_t v = 0; v < n_videos; v++)
+        if (frame_off[v + 1] < frame_off[v] || frame_off[0] != 0) B2_FAIL(B200NN_ERR_INVALID, "pq_query_groups: frame_off must ascend from 0");
+    if (!n_videos) return 0;
+    if (frame_off[n_videos] > 0 && !q_raw) B2_FAIL(B200NN_ERR_INVALID, "pq_query_groups: NULL queries");
+    Guard g(p);
+    Ctx* c = &p->ctx->c;
+    int rc;
+    if ((rc = ensure_csr(p))) return rc;
+    const long long ng = p->n_groups;
+    if (ng > 0xFFFFFFFFLL) B2_FAIL(B200NN_ERR_UNSUPPORTED, "pq_query_groups: more than 2^32 groups");
+    // frames of one video are scored in chunks of fc frames; the running per-video total is folded in frame order
+    const long long fc = std::max<long long>(1, std::min<long long>(256, (1LL << 28) / std::max<long long>(1, ng)));
+    if ((rc = p->ws_qraw.ensure((size_t)fc * p->D)) || (rc = p->ws_q.ensure((size_t)fc * p->D)) ||
+        (rc = p->ws_probes.ensure((size_t)fc * nprobe)) || (rc = p->ws_lut.ensure((size_t)fc * nprobe * p->M * p->ksub)) ||
+        (rc = p->ws_scores.ensure((size_t)(fc + 1) * std::max<long long>(1, ng))) || (rc = p->ws_keys.ensure(n_videos * k)) ||
+        (rc = p->ws_dist.ensure(n_videos * k)) || (rc = p->ws_id.ensure(n_videos * k)))
+        return rc;
+    float* total = p->ws_scores.p;            // row 0: running total (also frame_sum's "frame -1")
+    float* frames = p->ws_scores.p + ng;      // rows 1..fc: this chunk's per-frame scores
+    for (size_t v = 0; v < n_videos; v++) {
+        const long long f0 = frame_off[v], f1 = frame_off[v + 1];
+        if ((rc = launch_fill_f32(c, total, ng, 0.0f))) return rc;  // vector<float> score_total(img_num, 0.0f)
+        for (long long fa = f0; fa < f1; fa += fc) {
+            const long long cf = std::min<long long>(fc, f1 - fa);
+            B2_CUDA(cudaMemcpyAsync(p->ws_qraw.p, q_raw + fa * p->D, sizeof(float) * cf * p->D, cudaMemcpyHostToDevice, c->stream));
+            const float* qr = nullptr;
+            if ((rc = rotate_dev(p, p->ws_qraw.p, cf, p->ws_q.p, &qr))) return rc;
+            if ((rc = probes_and_luts(p, qr, cf, nprobe, p->ws_probes.p, p->ws_lut.p))) return rc;
+            if ((rc = launch_fill_f32(c, frames, cf * ng, p->clamp))) return rc;
+            if (ng && (rc = launch_ivf_scan(c, p->ws_lut.p, p->ws_probes.p, p->list_off.p, p->codes_sorted.p, p->group_sorted.p, p->M,
+                                            p->ksub, cf, nprobe, ng, frames)))
+                return rc;
+            // total = (((total + s[0]) + s[1]) + ...): row 0 of the buffer is the running total, 0.0f + x == x exactly
+            if ((rc = launch_frame_sum(c, total, (int)cf + 1, ng, total))) return rc;
+        }
+        if ((rc = launch_dense_topk(c, total, 1, ng, (int)k, p->ws_keys.p + v * k))) return rc;
+    }
+    if ((rc = launch_topk_merge(c, p->ws_keys.p, 1, (long long)n_videos, (int)k, (long long)(n_videos * k), p->ws_dist.p, nullptr,
+                                p->ws_id.p, nullptr)))
+        return rc;
+    B2_CUDA(cudaMemcpyAsync(out_score, p->ws_dist.p, sizeof(float) * n_videos * k, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaMemcpyAsync(out_group, p->ws_id.p, sizeof(uint64_t) * n_videos * k, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int b200nn_pq_search_dev(b200nn_pq_t p, const float* q_raw_dev, size_t nq, int nprobe, size_t k, float* out_dist_dev,
                          uint64_t* out_id_dev, uint64_t* out_key_dev, uint64_t id_base) {
     if (!p || (nq && !q_raw_dev)) B2_FAIL(B200NN_ERR_INVALID, "pq_search_dev: NULL argument");

@@ -30,6 +30,9 @@ int launch_adc_scan_topk(Ctx* ctx, int M, const uint32_t* codesT, const float* l
                          int n_full, int n_tail, const int* tail_desc_dev /* plan.desc on the device */, int k, float clamp,
                          uint32_t id_base, unsigned long long* out_keys, float* warm_scratch /* scan_warm_scratch_floats() floats */);
 int launch_fill_f32(Ctx* ctx, float* p, long long n, float v);
+// f-5: total[g] = sequential fp32 sum over frames of scores[f][g]; k smallest (value, index) per row of a dense matrix
+int launch_frame_sum(Ctx* ctx, const float* scores, int n_frames, long long ng, float* total);
+int launch_dense_topk(Ctx* ctx, const float* values, long long rows, long long n, int k, unsigned long long* out_keys);
 int launch_ivf_scan(Ctx* ctx, const float* lut, const int* probes, const long long* list_off, const unsigned char* codes_sorted,
                     const int* slot_sorted, int M, int ksub, long long nq, int nprobe, long long out_stride, float* out);
 int launch_ivf_search_topk(Ctx* ctx, const float* q_rot, long long nq, int D, const int* probes, int nprobe, const float* coarse,

@@ -7,10 +7,19 @@
 // tcgen05.ld brings 32 lanes x 32 columns to registers, d' = |x|^2 - 2 acc is compared with the
 // query's threshold, and the rare survivors go through the exact (dist, label) top-k lists.
 //
-// Roles (160 threads): warps 0-3 = epilogue (thread t owns query t = TMEM lane t, so a query's list is
-// touched by one warp only: no locks); warp 4, one elected thread = TMA producer + MMA issuer.
+// Roles (288 threads): warps 0-3 and 4-7 = two epilogue groups, group g drains accumulator g (the even / odd
+// tiles); inside a group thread t owns query t = TMEM lane t, so a list is touched by one warp only: no
+// locks, and each group emits its own sorted lists (2 output slices per CTA, merged by topk_merge_kernel).
+// Two groups = two warps per scheduler, which hides the dependent-ALU latency of the filter.  Warp 8, one
+// elected thread = TMA producer + MMA issuer.
+// All CTAs scanning slices for the same queries share a per-query upper bound on the k-th best distance in
+// global memory (atomicMin when a list's k-th improves, one relaxed load per tile): a row farther than the
+// k-th best of ANY partial list cannot be in the global top-k, so each CTA skips most of its own warm-up.
 //   B tiles (256 rows x D bytes) are stored in HBM already in the K-major no-swizzle core-matrix
-//   order (u8_rows_to_canonical_kernel), so a tile is ONE contiguous TMA bulk copy; |x|^2 rides along.
+//   order (u8_rows_to_canonical_kernel), so a tile is ONE contiguous TMA bulk copy; the rows' |x|^2 and
+//   label ranks ride along as a second 2 KB copy, so the epilogue never touches global memory.
+//   The epilogue keeps two tcgen05.ld of 32 columns in flight per warp (register double buffer) and
+//   filters a chunk with one running minimum per query; the exact mask is built only for chunks that hit.
 // Supported: D % 32 == 0, D <= 256, k <= 32 (otherwise the dp4a kernel of flat_kernels.cu is used).
 #include <stdint.h>
 
@@ -25,7 +34,10 @@ constexpr int TC_M = 128;      // queries per CTA (TMEM lanes)
 constexpr int TC_N = 256;      // database rows per tile
 constexpr int TC_KP = 32;      // list slots per query (k <= 32)
 constexpr int TC_SB = 8;       // staged records per query
-constexpr int TC_THREADS = 160;
+constexpr int TC_GROUPS = 2;   // epilogue groups (= accumulator buffers)
+constexpr int TC_THREADS = TC_GROUPS * 128 + 32;
+constexpr int TC_PRODUCER_WARP = TC_GROUPS * 4;
+constexpr int TC_META_BYTES = 2 * TC_N * 4;  // per tile: 256 x |x|^2 then 256 x label rank
 
 __device__ __forceinline__ uint64_t tc_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -72,23 +84,24 @@ __device__ __forceinline__ void warp_list_merge32(uint32_t L_addr, uint32_t cand
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32][8][16] canonical B tiles
-                  const int* __restrict__ xnorm,             // [tiles*256] |x|^2 (padded rows: large)
-                  const uint32_t* __restrict__ rank,         // [n] label rank of each row
+                  const int* __restrict__ xmeta,             // [tiles][2][256]: |x|^2 (padded rows: large), label rank
                   long long n, int D, const unsigned char* __restrict__ queries, long long nq, int n_slices, int k,
-                  unsigned long long* __restrict__ out_keys /*[slice][nq][k]*/) {
+                  int* __restrict__ gthr /*[nq] shared upper bound on the k-th best distance, pre-set to a large value*/,
+                  unsigned long long* __restrict__ out_keys /*[slice * 2 + group][nq][k]*/) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t A_BYTES = (uint32_t)TC_M * D, B_BYTES = (uint32_t)TC_N * D;
     const uint32_t sA = s_base;
     const uint32_t sB = sA + A_BYTES;                  // 2 stages
-    // |x|^2 ring: 4 stages, because a tile's norms are read by its epilogue, which may still run after
-    // the tile's shared-memory B stage has been released (the MMA retires first); stage t&3 is
-    // rewritten for tile t+4, whose load is issued only after the epilogue of tile t has signalled
-    const uint32_t sXN = sB + 2 * B_BYTES;             // 4 stages x 256 ints
-    const uint32_t sList = sXN + 4 * TC_N * 4;         // [128][32] keys
-    const uint32_t sStage = sList + TC_M * TC_KP * 8;  // [128][TC_SB] keys
-    const uint32_t sScratch = sStage + TC_M * TC_SB * 8;  // [4 warps][32 columns][32 lanes] words
-    const uint32_t bars = sScratch + 4 * 32 * 32 * 4;
+    // row-meta ring (|x|^2 + label rank): 4 stages, because a tile's meta is read by its epilogue, which may
+    // still run after the tile's shared-memory B stage has been released (the MMA retires first); stage t&3
+    // is rewritten for tile t+4, whose load is issued only after the epilogue of tile t has signalled
+    const uint32_t sXN = sB + 2 * B_BYTES;             // 4 stages x (256 norms + 256 ranks)
+    const uint32_t sList = sXN + 4 * TC_META_BYTES;                  // [groups][128][32] keys
+    const uint32_t sStage = sList + TC_GROUPS * TC_M * TC_KP * 8;    // [groups][128][TC_SB] keys
+    const uint32_t sScratch = sStage + TC_GROUPS * TC_M * TC_SB * 8;  // [8 warps][32 columns][32 lanes] words
+    const uint32_t sQn = sScratch + TC_GROUPS * 4 * 32 * 32 * 4;     // [128] |q|^2
+    const uint32_t bars = sQn + TC_M * 4;
     const uint32_t b_full = bars, b_empty = bars + 16, acc_full = bars + 32, acc_empty = bars + 48, tmem_slot = bars + 64;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long q0 = (long long)blockIdx.x * TC_M;
@@ -99,7 +112,7 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
     const uint32_t A_LBO = (TC_M / 8) * 128, B_LBO = (TC_N / 8) * 128, SBO = 128;
     const int ksteps = D / 32;
 
-    if (warp == 4) {
+    if (warp == TC_PRODUCER_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         if (lane == 0) {
@@ -113,8 +126,9 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
         }
     }
     // ---- queries -> canonical A tile, |q|^2, lists ----
-    int qn = 0;
+    for (int i = tid; i < TC_GROUPS * TC_M * TC_KP; i += TC_THREADS) sts64(sList + (uint32_t)i * 8u, KEY_MAX);
     if (tid < TC_M) {
+        int qn = 0;
         const long long qi = q0 + tid;
         const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
         for (int c = 0; c < D / 16; c++) {
@@ -127,7 +141,7 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
                          "r"(v.w)
                          : "memory");
         }
-        for (int j = 0; j < TC_KP; j++) sts64(sList + (uint32_t)(tid * TC_KP + j) * 8u, KEY_MAX);
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(sQn + (uint32_t)tid * 4u), "r"(qn) : "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -136,16 +150,16 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp == 4) {
+    if (warp == TC_PRODUCER_WARP) {
         // ===== TMA producer + MMA issuer (one thread) =====
         if (lane == 0 && T > 0) {
             // D = S32 (2<<4), A = B = unsigned 8-bit (0), K-major, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             auto load_tile = [&](int t) {
                 const int s = t & 1;
-                mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES + TC_N * 4);
+                mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES + TC_META_BYTES);
                 tma_load_1d(sB + (uint32_t)s * B_BYTES, xcan + (size_t)(t_lo + t) * B_BYTES, B_BYTES, b_full + 8 * s);
-                tma_load_1d(sXN + (uint32_t)(t & 3) * TC_N * 4, xnorm + (size_t)(t_lo + t) * TC_N, TC_N * 4, b_full + 8 * s);
+                tma_load_1d(sXN + (uint32_t)(t & 3) * TC_META_BYTES, xmeta + (size_t)(t_lo + t) * 2 * TC_N, TC_META_BYTES, b_full + 8 * s);
             };
             load_tile(0);
             for (int t = 0; t < T; t++) {
@@ -168,11 +182,15 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
             }
         }
     } else {
-        // ===== epilogue: thread t owns query t (TMEM lane t) =====
-        const bool qvalid = q0 + tid < nq;
-        const uint32_t myList = sList + (uint32_t)tid * TC_KP * 8u, myStage = sStage + (uint32_t)tid * TC_SB * 8u;
+        // ===== epilogue group g = warp / 4: thread owns query ql = tid % 128 (TMEM lane ql), tiles t % 2 == g =====
+        const int grp = warp >> 2, ql = tid & (TC_M - 1);
+        const bool qvalid = q0 + ql < nq;
+        const uint32_t myList = sList + (uint32_t)(grp * TC_M + ql) * TC_KP * 8u, myStage = sStage + (uint32_t)(grp * TC_M + ql) * TC_SB * 8u;
         const uint32_t warpList = sList + (uint32_t)(warp * 32) * TC_KP * 8u, warpStage = sStage + (uint32_t)(warp * 32) * TC_SB * 8u;
         const uint32_t scratch = sScratch + (uint32_t)warp * (32 * 32 * 4);
+        int qn;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(qn) : "r"(sQn + (uint32_t)ql * 4u));
+        int* my_gthr = gthr + (qvalid ? q0 + ql : 0);
         int cnt = 0;
         // tp = threshold on d' = |x|^2 - 2<q,x>  (dist - |q|^2); INT_MAX while the list is not full
         int tp = 0x7fffffff;
@@ -186,70 +204,95 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
                 if (lane == src) {
                     cnt = 0;
                     tkey = lds64(myList + (uint32_t)(k - 1) * 8u);
-                    tp = (tkey == KEY_MAX) ? 0x7fffffff : (s32_from_orderable((uint32_t)(tkey >> 32)) - qn);
+                    if (tkey != KEY_MAX) {  // list full: its k-th distance bounds the global k-th best
+                        const int kth = s32_from_orderable((uint32_t)(tkey >> 32));
+                        tp = min(tp, kth - qn);
+                        if (qvalid) atomicMin(my_gthr, kth);
+                    }
                 }
             }
         };
-        for (int t = 0; t < T; t++) {
-            const int s = t & 1, use = t >> 1;
-            mbar_wait(acc_full + 8 * s, (uint32_t)use & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const long long row_base = (t_lo + t) * TC_N;
-            const uint32_t xn_s = sXN + (uint32_t)(t & 3) * TC_N * 4;
-#pragma unroll 1
-            for (int c0 = 0; c0 < TC_N; c0 += 32) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * TC_N + c0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
-                      "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
-                      "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint32_t pm = 0;  // bit i: column c0+i passes this lane's threshold
+        auto tld32 = [&](uint32_t (&r)[32], uint32_t taddr) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+                  "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+                  "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+        };
+        // one chunk of 32 columns: d' = |x|^2 - 2 acc, one running minimum per query as the filter
+        auto process = [&](uint32_t (&r)[32], int c0, uint32_t meta_s, long long row_base) {
+            int mn = 0x7fffffff;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const uint4 xv = lds128(xn_s + (uint32_t)(c0 + i) * 4u);  // broadcast: |x|^2 of 4 columns
-                    r[i] = (uint32_t)((int)xv.x - 2 * (int)r[i]);
-                    r[i + 1] = (uint32_t)((int)xv.y - 2 * (int)r[i + 1]);
-                    r[i + 2] = (uint32_t)((int)xv.z - 2 * (int)r[i + 2]);
-                    r[i + 3] = (uint32_t)((int)xv.w - 2 * (int)r[i + 3]);
-                    if ((int)r[i] <= tp) pm |= 1u << i;
-                    if ((int)r[i + 1] <= tp) pm |= 2u << i;
-                    if ((int)r[i + 2] <= tp) pm |= 4u << i;
-                    if ((int)r[i + 3] <= tp) pm |= 8u << i;
-                }
-                if (!qvalid) pm = 0;
-                if (__any_sync(0xffffffffu, pm != 0)) {
-                    // park the chunk in the warp's scratch (word i*32+lane: conflict-free) so that the few
-                    // passing columns can be fetched by dynamic index
+            for (int i = 0; i < 32; i += 4) {
+                const uint4 xv = lds128(meta_s + (uint32_t)(c0 + i) * 4u);  // broadcast: |x|^2 of 4 columns
+                r[i] = (uint32_t)((int)xv.x - 2 * (int)r[i]);
+                r[i + 1] = (uint32_t)((int)xv.y - 2 * (int)r[i + 1]);
+                r[i + 2] = (uint32_t)((int)xv.z - 2 * (int)r[i + 2]);
+                r[i + 3] = (uint32_t)((int)xv.w - 2 * (int)r[i + 3]);
+                mn = min(mn, min((int)r[i], (int)r[i + 1]));
+                mn = min(mn, min((int)r[i + 2], (int)r[i + 3]));
+            }
+            const bool hit = qvalid && mn <= tp;
+            if (__any_sync(0xffffffffu, hit)) {
+                uint32_t pm = 0;  // bit i: column c0+i passes this lane's threshold
+                if (hit) {
 #pragma unroll
                     for (int i = 0; i < 32; i++)
-                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch + (uint32_t)(i * 32 + lane) * 4u), "r"(r[i]) : "memory");
-                    while (__any_sync(0xffffffffu, pm != 0)) {
-                        if (pm != 0 && cnt < TC_SB) {
-                            const int i = __ffs(pm) - 1;
-                            pm &= pm - 1;
-                            int dp;
-                            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(dp) : "r"(scratch + (uint32_t)(i * 32 + lane) * 4u));
-                            const long long row = row_base + c0 + i;
-                            if (dp <= tp && row < n) {  // tp may have tightened since the mask was built
-                                const unsigned long long key = make_key(s32_orderable(dp + qn), __ldg(rank + row));
-                                if (key < tkey) {
-                                    sts64(myStage + (uint32_t)cnt * 8u, key);
-                                    cnt++;
-                                }
+                        if ((int)r[i] <= tp) pm |= 1u << i;
+                }
+                // park the chunk in the warp's scratch (word i*32+lane: conflict-free) so that the few
+                // passing columns can be fetched by dynamic index
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch + (uint32_t)(i * 32 + lane) * 4u), "r"(r[i]) : "memory");
+                while (__any_sync(0xffffffffu, pm != 0)) {
+                    if (pm != 0 && cnt < TC_SB) {
+                        const int i = __ffs(pm) - 1;
+                        pm &= pm - 1;
+                        int dp;
+                        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(dp) : "r"(scratch + (uint32_t)(i * 32 + lane) * 4u));
+                        const long long row = row_base + c0 + i;
+                        if (dp <= tp && row < n) {  // tp may have tightened since the mask was built
+                            uint32_t rk;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rk) : "r"(meta_s + (uint32_t)(TC_N + c0 + i) * 4u));
+                            const unsigned long long key = make_key(s32_orderable(dp + qn), rk);
+                            if (key < tkey) {
+                                sts64(myStage + (uint32_t)cnt * 8u, key);
+                                cnt++;
                             }
                         }
-                        const unsigned full = __ballot_sync(0xffffffffu, cnt == TC_SB);
-                        if (full) flush(full);
                     }
-                    const unsigned soft = __ballot_sync(0xffffffffu, cnt >= TC_SB / 2);
-                    if (soft) flush(soft);
+                    const unsigned full = __ballot_sync(0xffffffffu, cnt == TC_SB);
+                    if (full) flush(full);
                 }
+                const unsigned soft = __ballot_sync(0xffffffffu, cnt >= TC_SB / 2);
+                if (soft) flush(soft);
+            }
+        };
+        for (int t = grp; t < T; t += TC_GROUPS) {
+            const int s = t & 1, use = t >> 1;
+            // the bound the other CTAs (and the other group) have reached for this query; a stale value is only looser
+            const int tg = *reinterpret_cast<volatile int*>(my_gthr);
+            mbar_wait(acc_full + 8 * s, (uint32_t)use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tg != 0x7f7f7f7f) tp = min(tp, tg - qn);
+            const long long row_base = (t_lo + t) * TC_N;
+            const uint32_t meta_s = sXN + (uint32_t)(t & 3) * TC_META_BYTES;
+            const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * TC_N);
+            uint32_t ra[32], rb[32];
+            tld32(ra, tacc);
+#pragma unroll 1
+            for (int c0 = 0; c0 < TC_N; c0 += 64) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tld32(rb, tacc + (uint32_t)(c0 + 32));  // in flight while chunk c0 is filtered
+                process(ra, c0, meta_s, row_base);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 64 < TC_N) tld32(ra, tacc + (uint32_t)(c0 + 64));
+                process(rb, c0 + 32, meta_s, row_base);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -257,16 +300,17 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
         }
         flush(__ballot_sync(0xffffffffu, cnt > 0));
         if (qvalid)
-            for (int j = 0; j < k; j++) out_keys[((long long)slice * nq + q0 + tid) * k + j] = lds64(myList + (uint32_t)j * 8u);
+            for (int j = 0; j < k; j++)
+                out_keys[((long long)(slice * TC_GROUPS + grp) * nq + q0 + ql) * k + j] = lds64(myList + (uint32_t)j * 8u);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (warp == TC_PRODUCER_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-// row-major u8 rows -> canonical B tiles + |x|^2
-__global__ void u8_rows_to_canonical_kernel(const unsigned char* __restrict__ rows, long long n, int D, unsigned char* __restrict__ xcan,
-                                            int* __restrict__ xnorm, long long n_pad) {
+// row-major u8 rows -> canonical B tiles + per-tile row meta (|x|^2, label rank)
+__global__ void u8_rows_to_canonical_kernel(const unsigned char* __restrict__ rows, const uint32_t* __restrict__ rank, long long n, int D,
+                                            unsigned char* __restrict__ xcan, int* __restrict__ xmeta, long long n_pad) {
     // one thread per (row, 16-byte chunk)
     const int chunks = D / 16;
     const long long total = n_pad * chunks;
@@ -289,17 +333,21 @@ __global__ void u8_rows_to_canonical_kernel(const unsigned char* __restrict__ ro
                 s += v * v;
             }
         }
-        xnorm[row] = s;
+        const long long tile = row / TC_N;
+        const int rl = (int)(row - tile * TC_N);
+        xmeta[tile * 2 * TC_N + rl] = s;
+        xmeta[tile * 2 * TC_N + TC_N + rl] = row < n ? (int)rank[row] : -1;
     }
 }
 
 bool u8_scan_tc_supported(int D, int k) { return D % 32 == 0 && D >= 32 && D <= 256 && k >= 1 && k <= TC_KP; }
 
-int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, long long n, int D, unsigned char* xcan, int* xnorm, long long n_pad) {
+int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint32_t* rank, long long n, int D, unsigned char* xcan,
+                                int* xmeta, long long n_pad) {
     if (n_pad <= 0) return 0;
     const long long work = n_pad * (D / 16);
     u8_rows_to_canonical_kernel<<<(unsigned)std::max<long long>(1, std::min<long long>((work + 255) / 256, (long long)ctx->sm_count * 16)), 256,
-                                  0, ctx->stream>>>(rows, n, D, xcan, xnorm, n_pad);
+                                  0, ctx->stream>>>(rows, rank, n, D, xcan, xmeta, n_pad);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;
@@ -312,14 +360,18 @@ int u8_scan_tc_slices(int sm_count, long long nq, long long n) {
     return (int)std::min<long long>(s, 1024);
 }
 
-int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xnorm, const uint32_t* rank, long long n, int D,
-                      const unsigned char* queries, long long nq, int n_slices, int k, unsigned long long* out_keys) {
+int u8_scan_tc_lists_per_slice() { return TC_GROUPS; }
+
+int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, int D, const unsigned char* queries,
+                      long long nq, int n_slices, int k, int* gthr, unsigned long long* out_keys) {
     if (nq <= 0) return 0;
     if (!u8_scan_tc_supported(D, k)) B2_FAIL(-4, "u8 tensor-core scan: needs D % 32 == 0, D <= 256, k <= 32");
-    const size_t smem = (size_t)TC_M * D + 2 * (size_t)TC_N * D + 4 * TC_N * 4 + (size_t)TC_M * TC_KP * 8 + (size_t)TC_M * TC_SB * 8 + 4 * 32 * 32 * 4 + 128;
+    const size_t smem = (size_t)TC_M * D + 2 * (size_t)TC_N * D + 4 * TC_META_BYTES +
+                        TC_GROUPS * ((size_t)TC_M * TC_KP * 8 + (size_t)TC_M * TC_SB * 8 + 4 * 32 * 32 * 4) + TC_M * 4 + 128;
+    B2_CUDA(cudaMemsetAsync(gthr, 0x7f, sizeof(int) * nq, ctx->stream));  // 0x7f7f7f7f = "no bound yet"
     B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((nq + TC_M - 1) / TC_M), (unsigned)n_slices);
-    u8_scan_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(xcan, xnorm, rank, n, D, queries, nq, n_slices, k, out_keys);
+    u8_scan_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, gthr, out_keys);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

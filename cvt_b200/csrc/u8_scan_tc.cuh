@@ -5,11 +5,14 @@
 namespace b200nn {
 
 bool u8_scan_tc_supported(int D, int k);
-// rows [n][D] u8 -> canonical 256-row tiles + |x|^2 (both padded to n_pad = multiple of 256)
-int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, long long n, int D, unsigned char* xcan, int* xnorm, long long n_pad);
+// rows [n][D] u8 -> canonical 256-row tiles + per-tile row meta xmeta[tiles][2][256] = {|x|^2, label rank}
+// (n_pad = multiple of 256; xmeta holds 2 * n_pad ints)
+int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint32_t* rank, long long n, int D, unsigned char* xcan,
+                                int* xmeta, long long n_pad);
 int u8_scan_tc_slices(int sm_count, long long nq, long long n);
-// out_keys [n_slices][nq][k]; ids in the keys are label ranks
-int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xnorm, const uint32_t* rank, long long n, int D,
-                      const unsigned char* queries, long long nq, int n_slices, int k, unsigned long long* out_keys);
+int u8_scan_tc_lists_per_slice();
+// out_keys [n_slices * u8_scan_tc_lists_per_slice()][nq][k]; ids in the keys are label ranks; gthr = nq ints of scratch
+int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, int D, const unsigned char* queries,
+                      long long nq, int n_slices, int k, int* gthr, unsigned long long* out_keys);
 
 }  // namespace b200nn

@@ -106,6 +106,13 @@ int b200nn_pq_build_lut(b200nn_pq_t idx, const float* q_rotated, size_t nq, int 
                         float* out_lut);
 /* IVFOPQ::QueryThrehold: out_scores [nq, n_groups], clamp-initialised, min-aggregated per group. */
 int b200nn_pq_scores(b200nn_pq_t idx, const float* q_raw, size_t nq, int nprobe, float* out_scores);
+/* What the reference's query main does with Query's output (opq/src/multi_frame_index_test.cpp:54-68): query
+ * video v = frames [frame_off[v], frame_off[v+1]) of q_raw; per frame the QueryThrehold scores (above), summed
+ * over the video's frames per indexed videoId in frame order (fp32, from 0.0f), then get_sort_results
+ * (opq/src/common.h:25-37): the k smallest (score, videoId), ascending.  out_* are [n_videos, k]; when fewer than k
+ * videos are indexed the tail is (+inf, UINT64_MAX).  Only the results leave the device. */
+int b200nn_pq_query_groups(b200nn_pq_t idx, const float* q_raw, const int64_t* frame_off, size_t n_videos, int nprobe, size_t k,
+                           float* out_score, uint64_t* out_group);
 /* a1,a4,a5,a6,a7 fused: per-row ADC scores (clamped) -> k smallest under (score,row), ascending.
  * out_id = id_base + row index.  K==1 runs the TMA-staged conflict-free scan kernel. */
 int b200nn_pq_search(b200nn_pq_t idx, const float* q_raw, size_t nq, int nprobe, size_t k, float* out_dist,
