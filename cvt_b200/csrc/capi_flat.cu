@@ -30,7 +30,6 @@ struct b200nn_flat {
     long long tc_rows = -1;
     DevBuf<unsigned char> xcan;
     DevBuf<int> xnorm;   // per-tile row meta: |x|^2 and label rank
-    DevBuf<int> ws_thr;  // per-query shared distance bound of the tensor-core scan
     DevBuf<unsigned char> ws_q;
     DevBuf<unsigned long long> ws_keys, ws_id;
     DevBuf<float> ws_dist;
@@ -100,10 +99,10 @@ int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, vo
             if ((rc = launch_u8_rows_to_canonical(c, p->data.p, p->rank.p, (long long)p->n, (int)p->dim, p->xcan.p, p->xnorm.p, n_pad))) return rc;
             p->tc_rows = (long long)p->n;
         }
-        const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, (long long)p->n), L = S * u8_scan_tc_lists_per_slice();
-        if ((rc = p->ws_keys.ensure((size_t)L * nq * k)) || (rc = p->ws_thr.ensure(nq))) return rc;
+        const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, (long long)p->n), L = S * u8_scan_tc_lists_per_slice((int)p->dim, (int)k);
+        if ((rc = p->ws_keys.ensure((size_t)L * nq * k))) return rc;
         if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, (long long)p->n, (int)p->dim, (const unsigned char*)q_dev, (long long)nq, S,
-                                    (int)k, p->ws_thr.p, p->ws_keys.p)))
+                                    (int)k, p->ws_keys.p)))
             return rc;
         if ((rc = launch_topk_merge(c, p->ws_keys.p, L, (long long)nq, (int)k, (long long)(nq * k), nullptr, (int*)out_dist, out_label, nullptr)))
             return rc;

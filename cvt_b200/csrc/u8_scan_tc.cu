@@ -7,14 +7,14 @@
 // tcgen05.ld brings 32 lanes x 32 columns to registers, d' = |x|^2 - 2 acc is compared with the
 // query's threshold, and the rare survivors go through the exact (dist, label) top-k lists.
 //
-// Roles (288 threads): warps 0-3 and 4-7 = two epilogue groups, group g drains accumulator g (the even / odd
-// tiles); inside a group thread t owns query t = TMEM lane t, so a list is touched by one warp only: no
-// locks, and each group emits its own sorted lists (2 output slices per CTA, merged by topk_merge_kernel).
-// Two groups = two warps per scheduler, which hides the dependent-ALU latency of the filter.  Warp 8, one
-// elected thread = TMA producer + MMA issuer.
-// All CTAs scanning slices for the same queries share a per-query upper bound on the k-th best distance in
-// global memory (atomicMin when a list's k-th improves, one relaxed load per tile): a row farther than the
-// k-th best of ANY partial list cannot be in the global top-k, so each CTA skips most of its own warm-up.
+// Roles (288 threads): warps 0-3 and 4-7 = two epilogue groups, group g drains columns [128 g, 128 g + 128)
+// of every accumulator (so the MMA of the next tile always overlaps the drain of this one); inside a group
+// thread t owns query t = TMEM lane t and keeps that query's sorted list PRIVATE: survivors are inserted at
+// once by the owning thread -- no staging, no locks, no warp collectives -- and each group emits its own
+// lists (2 output slices per CTA, merged by topk_merge_kernel).  Two groups = two warps per scheduler, which
+// hides the dependent-ALU latency of the filter.  Warp 8, one elected thread = TMA producer + MMA issuer.
+// (Measured and dropped: sharing a per-query distance bound between the CTAs of different slices through
+// global atomics -- the k-th best of a partial list bounds the global k-th only as well as ONE slice does.)
 //   B tiles (256 rows x D bytes) are stored in HBM already in the K-major no-swizzle core-matrix
 //   order (u8_rows_to_canonical_kernel), so a tile is ONE contiguous TMA bulk copy; the rows' |x|^2 and
 //   label ranks ride along as a second 2 KB copy, so the epilogue never touches global memory.
@@ -33,10 +33,7 @@ namespace b200nn {
 constexpr int TC_M = 128;      // queries per CTA (TMEM lanes)
 constexpr int TC_N = 256;      // database rows per tile
 constexpr int TC_KP = 32;      // list slots per query (k <= 32)
-constexpr int TC_SB = 8;       // staged records per query
-constexpr int TC_GROUPS = 2;   // epilogue groups (= accumulator buffers)
-constexpr int TC_THREADS = TC_GROUPS * 128 + 32;
-constexpr int TC_PRODUCER_WARP = TC_GROUPS * 4;
+constexpr int TC_MAX_SMEM = 232448;  // 227 KB
 constexpr int TC_META_BYTES = 2 * TC_N * 4;  // per tile: 256 x |x|^2 then 256 x label rank
 
 __device__ __forceinline__ uint64_t tc_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -59,34 +56,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// rank-merge of nb (<= TC_SB) candidates into a sorted list of 32 keys (one per lane); warp-private list
-__device__ __forceinline__ void warp_list_merge32(uint32_t L_addr, uint32_t cand_addr, int nb) {
-    const int lane = threadIdx.x & 31;
-    const unsigned long long l = lds64(L_addr + (uint32_t)lane * 8u);
-    const unsigned long long c = lane < nb ? lds64(cand_addr + (uint32_t)lane * 8u) : KEY_MAX;
-    int pl = 0, pc = 0;
-    for (int j = 0; j < nb; j++) {
-        const unsigned long long cj = lds64(cand_addr + (uint32_t)j * 8u);
-        pl += (cj < l) ? 1 : 0;
-        pc += (cj < c) ? 1 : 0;
+// Insert `key` (smaller than the current k-th entry, distinct from every entry) into a THREAD-private ascending
+// list of k <= 32 keys in shared memory; returns the new k-th entry.
+__device__ __forceinline__ unsigned long long list_insert32(uint32_t L_addr, unsigned long long key, int k) {
+    int j = k - 1;
+    while (j > 0) {
+        const unsigned long long prev = lds64(L_addr + (uint32_t)(j - 1) * 8u);
+        if (prev < key) break;
+        sts64(L_addr + (uint32_t)j * 8u, prev);
+        j--;
     }
-    int pos = 0;
-#pragma unroll
-    for (int step = TC_KP / 2; step >= 1; step >>= 1)
-        if (lds64(L_addr + (uint32_t)(pos + step - 1) * 8u) < c) pos += step;
-    if (lds64(L_addr + (uint32_t)pos * 8u) < c) pos += 1;
-    pc += pos;
-    __syncwarp();
-    if (lane + pl < TC_KP) sts64(L_addr + (uint32_t)(lane + pl) * 8u, l);
-    if (lane < nb && pc < TC_KP) sts64(L_addr + (uint32_t)pc * 8u, c);
-    __syncwarp();
+    sts64(L_addr + (uint32_t)j * 8u, key);
+    return lds64(L_addr + (uint32_t)(k - 1) * 8u);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int TC_GROUPS>
+__global__ void __launch_bounds__(TC_GROUPS * 128 + 32, 1)
 u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32][8][16] canonical B tiles
                   const int* __restrict__ xmeta,             // [tiles][2][256]: |x|^2 (padded rows: large), label rank
                   long long n, int D, const unsigned char* __restrict__ queries, long long nq, int n_slices, int k,
-                  int* __restrict__ gthr /*[nq] shared upper bound on the k-th best distance, pre-set to a large value*/,
                   unsigned long long* __restrict__ out_keys /*[slice * 2 + group][nq][k]*/) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
@@ -97,10 +85,10 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
     // still run after the tile's shared-memory B stage has been released (the MMA retires first); stage t&3
     // is rewritten for tile t+4, whose load is issued only after the epilogue of tile t has signalled
     const uint32_t sXN = sB + 2 * B_BYTES;             // 4 stages x (256 norms + 256 ranks)
-    const uint32_t sList = sXN + 4 * TC_META_BYTES;                  // [groups][128][32] keys
-    const uint32_t sStage = sList + TC_GROUPS * TC_M * TC_KP * 8;    // [groups][128][TC_SB] keys
-    const uint32_t sScratch = sStage + TC_GROUPS * TC_M * TC_SB * 8;  // [8 warps][32 columns][32 lanes] words
-    const uint32_t sQn = sScratch + TC_GROUPS * 4 * 32 * 32 * 4;     // [128] |q|^2
+    const uint32_t sList = sXN + 4 * TC_META_BYTES;                  // [groups][128][k] keys
+    constexpr int TC_THREADS = TC_GROUPS * 128 + 32, TC_PRODUCER_WARP = TC_GROUPS * 4;
+    const uint32_t sScratch = sList + (uint32_t)(TC_GROUPS * TC_M * k) * 8u;   // [warps][32 columns][32 lanes] words
+    const uint32_t sQn = sScratch + TC_GROUPS * 4 * 32 * 32 * 4;             // [128] |q|^2
     const uint32_t bars = sQn + TC_M * 4;
     const uint32_t b_full = bars, b_empty = bars + 16, acc_full = bars + 32, acc_empty = bars + 48, tmem_slot = bars + 64;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -120,13 +108,13 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
                 mbar_init(b_full + 8 * i, 1);
                 mbar_init(b_empty + 8 * i, 1);
                 mbar_init(acc_full + 8 * i, 1);
-                mbar_init(acc_empty + 8 * i, 4);  // one arrival per epilogue warp
+                mbar_init(acc_empty + 8 * i, TC_GROUPS * 4);  // one arrival per epilogue warp
             }
             mbar_fence_init();
         }
     }
     // ---- queries -> canonical A tile, |q|^2, lists ----
-    for (int i = tid; i < TC_GROUPS * TC_M * TC_KP; i += TC_THREADS) sts64(sList + (uint32_t)i * 8u, KEY_MAX);
+    for (int i = tid; i < TC_GROUPS * TC_M * k; i += TC_THREADS) sts64(sList + (uint32_t)i * 8u, KEY_MAX);
     if (tid < TC_M) {
         int qn = 0;
         const long long qi = q0 + tid;
@@ -182,36 +170,16 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
             }
         }
     } else {
-        // ===== epilogue group g = warp / 4: thread owns query ql = tid % 128 (TMEM lane ql), tiles t % 2 == g =====
+        // ===== epilogue group g = warp / 4: thread owns query ql = tid % 128 (TMEM lane ql), columns [128 g, 128 g + 128) of every tile =====
         const int grp = warp >> 2, ql = tid & (TC_M - 1);
         const bool qvalid = q0 + ql < nq;
-        const uint32_t myList = sList + (uint32_t)(grp * TC_M + ql) * TC_KP * 8u, myStage = sStage + (uint32_t)(grp * TC_M + ql) * TC_SB * 8u;
-        const uint32_t warpList = sList + (uint32_t)(warp * 32) * TC_KP * 8u, warpStage = sStage + (uint32_t)(warp * 32) * TC_SB * 8u;
-        const uint32_t scratch = sScratch + (uint32_t)warp * (32 * 32 * 4);
+        const uint32_t myList = sList + (uint32_t)((grp * TC_M + ql) * k) * 8u;
+        const uint32_t scratch = sScratch + (uint32_t)warp * (32 * 32 * 4) + (uint32_t)lane * 4u;
         int qn;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(qn) : "r"(sQn + (uint32_t)ql * 4u));
-        int* my_gthr = gthr + (qvalid ? q0 + ql : 0);
-        int cnt = 0;
         // tp = threshold on d' = |x|^2 - 2<q,x>  (dist - |q|^2); INT_MAX while the list is not full
         int tp = 0x7fffffff;
         unsigned long long tkey = KEY_MAX;
-        auto flush = [&](unsigned need) {
-            while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                const int nb = __shfl_sync(0xffffffffu, cnt, src);
-                warp_list_merge32(warpList + (uint32_t)src * TC_KP * 8u, warpStage + (uint32_t)src * TC_SB * 8u, nb);
-                if (lane == src) {
-                    cnt = 0;
-                    tkey = lds64(myList + (uint32_t)(k - 1) * 8u);
-                    if (tkey != KEY_MAX) {  // list full: its k-th distance bounds the global k-th best
-                        const int kth = s32_from_orderable((uint32_t)(tkey >> 32));
-                        tp = min(tp, kth - qn);
-                        if (qvalid) atomicMin(my_gthr, kth);
-                    }
-                }
-            }
-        };
         auto tld32 = [&](uint32_t (&r)[32], uint32_t taddr) {
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -223,7 +191,9 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
                 : "r"(taddr)
                 : "memory");
         };
-        // one chunk of 32 columns: d' = |x|^2 - 2 acc, one running minimum per query as the filter
+        // one chunk of 32 columns: d' = |x|^2 - 2 acc, one running minimum per query as the filter; a query
+        // that hits walks its 32 values and inserts the survivors straight into its own sorted list
+        // (thread-private: no staging, no warp collectives, the threshold tightens at once)
         auto process = [&](uint32_t (&r)[32], int c0, uint32_t meta_s, long long row_base) {
             int mn = 0x7fffffff;
 #pragma unroll
@@ -236,69 +206,56 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
                 mn = min(mn, min((int)r[i], (int)r[i + 1]));
                 mn = min(mn, min((int)r[i + 2], (int)r[i + 3]));
             }
-            const bool hit = qvalid && mn <= tp;
-            if (__any_sync(0xffffffffu, hit)) {
-                uint32_t pm = 0;  // bit i: column c0+i passes this lane's threshold
-                if (hit) {
+            if (qvalid && mn <= tp) {
+                // park this lane's 32 values (word i*32+lane: conflict-free) so that the few passing columns can be
+                // fetched by dynamic index, and walk the mask of passing columns
+                uint32_t pm = 0;
 #pragma unroll
-                    for (int i = 0; i < 32; i++)
-                        if ((int)r[i] <= tp) pm |= 1u << i;
+                for (int i = 0; i < 32; i++) {
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch + (uint32_t)(i * 128)), "r"(r[i]) : "memory");
+                    if ((int)r[i] <= tp) pm |= 1u << i;
                 }
-                // park the chunk in the warp's scratch (word i*32+lane: conflict-free) so that the few
-                // passing columns can be fetched by dynamic index
-#pragma unroll
-                for (int i = 0; i < 32; i++)
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch + (uint32_t)(i * 32 + lane) * 4u), "r"(r[i]) : "memory");
-                while (__any_sync(0xffffffffu, pm != 0)) {
-                    if (pm != 0 && cnt < TC_SB) {
-                        const int i = __ffs(pm) - 1;
-                        pm &= pm - 1;
-                        int dp;
-                        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(dp) : "r"(scratch + (uint32_t)(i * 32 + lane) * 4u));
-                        const long long row = row_base + c0 + i;
-                        if (dp <= tp && row < n) {  // tp may have tightened since the mask was built
-                            uint32_t rk;
-                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rk) : "r"(meta_s + (uint32_t)(TC_N + c0 + i) * 4u));
-                            const unsigned long long key = make_key(s32_orderable(dp + qn), rk);
-                            if (key < tkey) {
-                                sts64(myStage + (uint32_t)cnt * 8u, key);
-                                cnt++;
-                            }
+                while (pm) {
+                    const int i = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    int dp;
+                    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(dp) : "r"(scratch + (uint32_t)(i * 128)));
+                    if (dp <= tp && row_base + c0 + i < n) {  // tp may have tightened since the mask was built
+                        uint32_t rk;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rk) : "r"(meta_s + (uint32_t)(TC_N + c0 + i) * 4u));
+                        const unsigned long long key = make_key(s32_orderable(dp + qn), rk);
+                        if (key < tkey) {
+                            tkey = list_insert32(myList, key, k);
+                            if (tkey != KEY_MAX) tp = s32_from_orderable((uint32_t)(tkey >> 32)) - qn;  // list full: k-th distance
                         }
                     }
-                    const unsigned full = __ballot_sync(0xffffffffu, cnt == TC_SB);
-                    if (full) flush(full);
                 }
-                const unsigned soft = __ballot_sync(0xffffffffu, cnt >= TC_SB / 2);
-                if (soft) flush(soft);
             }
+            __syncwarp();
         };
-        for (int t = grp; t < T; t += TC_GROUPS) {
+        for (int t = 0; t < T; t++) {
             const int s = t & 1, use = t >> 1;
-            // the bound the other CTAs (and the other group) have reached for this query; a stale value is only looser
-            const int tg = *reinterpret_cast<volatile int*>(my_gthr);
             mbar_wait(acc_full + 8 * s, (uint32_t)use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (tg != 0x7f7f7f7f) tp = min(tp, tg - qn);
             const long long row_base = (t_lo + t) * TC_N;
             const uint32_t meta_s = sXN + (uint32_t)(t & 3) * TC_META_BYTES;
-            const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * TC_N);
+            const int cg = grp * (TC_N / TC_GROUPS);
+            const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * TC_N + cg);
             uint32_t ra[32], rb[32];
             tld32(ra, tacc);
 #pragma unroll 1
-            for (int c0 = 0; c0 < TC_N; c0 += 64) {
+            for (int c0 = 0; c0 < TC_N / TC_GROUPS; c0 += 64) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 tld32(rb, tacc + (uint32_t)(c0 + 32));  // in flight while chunk c0 is filtered
-                process(ra, c0, meta_s, row_base);
+                process(ra, cg + c0, meta_s, row_base);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 64 < TC_N) tld32(ra, tacc + (uint32_t)(c0 + 64));
-                process(rb, c0 + 32, meta_s, row_base);
+                if (c0 + 64 < TC_N / TC_GROUPS) tld32(ra, tacc + (uint32_t)(c0 + 64));
+                process(rb, cg + c0 + 32, meta_s, row_base);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * s);
         }
-        flush(__ballot_sync(0xffffffffu, cnt > 0));
         if (qvalid)
             for (int j = 0; j < k; j++)
                 out_keys[((long long)(slice * TC_GROUPS + grp) * nq + q0 + ql) * k + j] = lds64(myList + (uint32_t)j * 8u);
@@ -340,7 +297,15 @@ __global__ void u8_rows_to_canonical_kernel(const unsigned char* __restrict__ ro
     }
 }
 
-bool u8_scan_tc_supported(int D, int k) { return D % 32 == 0 && D >= 32 && D <= 256 && k >= 1 && k <= TC_KP; }
+static size_t tc_smem_bytes(int D, int k, int groups) {
+    return (size_t)TC_M * D + 2 * (size_t)TC_N * D + 4 * TC_META_BYTES + (size_t)groups * (TC_M * (size_t)k * 8 + 4 * 32 * 32 * 4) + TC_M * 4 + 128;
+}
+// two epilogue groups when their lists and scratch fit beside the operand tiles, else one
+int u8_scan_tc_lists_per_slice(int D, int k) { return tc_smem_bytes(D, k, 2) <= (size_t)TC_MAX_SMEM ? 2 : 1; }
+
+bool u8_scan_tc_supported(int D, int k) {
+    return D % 32 == 0 && D >= 32 && D <= 256 && k >= 1 && k <= TC_KP && tc_smem_bytes(D, k, 1) <= (size_t)TC_MAX_SMEM;
+}
 
 int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint32_t* rank, long long n, int D, unsigned char* xcan,
                                 int* xmeta, long long n_pad) {
@@ -360,18 +325,20 @@ int u8_scan_tc_slices(int sm_count, long long nq, long long n) {
     return (int)std::min<long long>(s, 1024);
 }
 
-int u8_scan_tc_lists_per_slice() { return TC_GROUPS; }
-
 int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, int D, const unsigned char* queries,
-                      long long nq, int n_slices, int k, int* gthr, unsigned long long* out_keys) {
+                      long long nq, int n_slices, int k, unsigned long long* out_keys) {
     if (nq <= 0) return 0;
     if (!u8_scan_tc_supported(D, k)) B2_FAIL(-4, "u8 tensor-core scan: needs D % 32 == 0, D <= 256, k <= 32");
-    const size_t smem = (size_t)TC_M * D + 2 * (size_t)TC_N * D + 4 * TC_META_BYTES +
-                        TC_GROUPS * ((size_t)TC_M * TC_KP * 8 + (size_t)TC_M * TC_SB * 8 + 4 * 32 * 32 * 4) + TC_M * 4 + 128;
-    B2_CUDA(cudaMemsetAsync(gthr, 0x7f, sizeof(int) * nq, ctx->stream));  // 0x7f7f7f7f = "no bound yet"
-    B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int groups = u8_scan_tc_lists_per_slice(D, k);
+    const size_t smem = tc_smem_bytes(D, k, groups);
     dim3 grid((unsigned)((nq + TC_M - 1) / TC_M), (unsigned)n_slices);
-    u8_scan_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, gthr, out_keys);
+    if (groups == 2) {
+        B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        u8_scan_tc_kernel<2><<<grid, 2 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, out_keys);
+    } else {
+        B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        u8_scan_tc_kernel<1><<<grid, 1 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, out_keys);
+    }
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

@@ -10,9 +10,9 @@ bool u8_scan_tc_supported(int D, int k);
 int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint32_t* rank, long long n, int D, unsigned char* xcan,
                                 int* xmeta, long long n_pad);
 int u8_scan_tc_slices(int sm_count, long long nq, long long n);
-int u8_scan_tc_lists_per_slice();
-// out_keys [n_slices * u8_scan_tc_lists_per_slice()][nq][k]; ids in the keys are label ranks; gthr = nq ints of scratch
+int u8_scan_tc_lists_per_slice(int D, int k);
+// out_keys [n_slices * u8_scan_tc_lists_per_slice(D, k)][nq][k]; ids in the keys are label ranks
 int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, int D, const unsigned char* queries,
-                      long long nq, int n_slices, int k, int* gthr, unsigned long long* out_keys);
+                      long long nq, int n_slices, int k, unsigned long long* out_keys);
 
 }  // namespace b200nn
