@@ -30,6 +30,7 @@ struct b200nn_flat {
     long long tc_rows = -1;
     DevBuf<unsigned char> xcan;
     DevBuf<int> xnorm;   // per-tile row meta: |x|^2 and label rank
+    DevBuf<int> ws_thr;  // [nq][k] distances of the sample pass (column k-1 = the bound the full pass starts from)
     DevBuf<unsigned char> ws_q;
     DevBuf<unsigned long long> ws_keys, ws_id;
     DevBuf<float> ws_dist;
@@ -99,10 +100,28 @@ int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, vo
             if ((rc = launch_u8_rows_to_canonical(c, p->data.p, p->rank.p, (long long)p->n, (int)p->dim, p->xcan.p, p->xnorm.p, n_pad))) return rc;
             p->tc_rows = (long long)p->n;
         }
-        const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, (long long)p->n), L = S * u8_scan_tc_lists_per_slice((int)p->dim, (int)k);
+        const int groups = u8_scan_tc_lists_per_slice((int)p->dim, (int)k);
+        const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, (long long)p->n), L = S * groups;
         if ((rc = p->ws_keys.ensure((size_t)L * nq * k))) return rc;
+        // Every (slice, group) list pays its own top-k warm-up of ~k ln(rows/k) insertions.  For a large index a first
+        // pass over a 16 k-row prefix yields each query's exact k-th best distance there -- an upper bound on its global
+        // k-th best -- and the full pass starts from that bound instead of +inf (exact: ties at the bound are kept).
+        const long long n_sample = 16384;
+        const int* init_thr = nullptr;
+        if ((long long)p->n >= 16 * n_sample && !getenv("B200NN_NO_U8_SAMPLE")) {
+            const int Sa = u8_scan_tc_slices(c->sm_count, (long long)nq, n_sample);
+            if (Sa * groups > L) B2_FAIL(B200NN_ERR_STATE, "flat_search: sample pass needs more lists than the full pass");
+            if ((rc = p->ws_thr.ensure(nq * k))) return rc;
+            if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, n_sample, (int)p->dim, (const unsigned char*)q_dev, (long long)nq, Sa,
+                                        (int)k, nullptr, 0, p->ws_keys.p)))
+                return rc;
+            if ((rc = launch_topk_merge(c, p->ws_keys.p, Sa * groups, (long long)nq, (int)k, (long long)(nq * k), nullptr, p->ws_thr.p, nullptr,
+                                        nullptr)))
+                return rc;
+            init_thr = p->ws_thr.p + (k - 1);
+        }
         if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, (long long)p->n, (int)p->dim, (const unsigned char*)q_dev, (long long)nq, S,
-                                    (int)k, p->ws_keys.p)))
+                                    (int)k, init_thr, (int)k, p->ws_keys.p)))
             return rc;
         if ((rc = launch_topk_merge(c, p->ws_keys.p, L, (long long)nq, (int)k, (long long)(nq * k), nullptr, (int*)out_dist, out_label, nullptr)))
             return rc;

@@ -63,9 +63,67 @@ __global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Many short lists (L * k <= 512 keys, e.g. the 36 x 10 lists of the u8 tensor-core scan): the rank merge above
+// would spend (L - 1) binary searches per key.  Here every lane keeps <= 16 of the query's keys in registers and
+// the warp extracts the minimum k times (lane-local minimum + shuffle minimum); order inside the lists is
+// irrelevant.  Keys are distinct apart from the KEY_MAX padding.  Same layout and outputs as topk_merge_kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void topk_merge_extract_kernel(const unsigned long long* __restrict__ keys, int L, long long nq, int k,
+                                          long long list_stride, float* __restrict__ out_dist_f, int* __restrict__ out_dist_i,
+                                          unsigned long long* __restrict__ out_id, unsigned long long* __restrict__ out_key) {
+    constexpr int E = 16;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + w;
+    if (q >= nq) return;
+    const long long cq = list_stride / k, chunk = q / cq;
+    const unsigned long long* base = keys + (chunk * (L - 1) * cq + q) * k;
+    unsigned long long x[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int idx = e * 32 + lane;
+        x[e] = KEY_MAX;
+        if (idx < L * k) {
+            const int l = idx / k, j = idx - l * k;
+            x[e] = __ldg(base + (long long)l * list_stride + j);
+        }
+    }
+    for (int r = 0; r < k; r++) {
+        unsigned long long m = x[0];
+#pragma unroll
+        for (int e = 1; e < E; e++) m = x[e] < m ? x[e] : m;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, s);
+            m = o < m ? o : m;
+        }
+        if (m != KEY_MAX) {
+#pragma unroll
+            for (int e = 0; e < E; e++) x[e] = (x[e] == m) ? KEY_MAX : x[e];
+        }
+        if (lane == (r & 31)) {
+            const long long o = q * k + r;
+            const uint32_t ord = (uint32_t)(m >> 32);
+            const bool real = m != KEY_MAX;
+            if (out_dist_f) out_dist_f[o] = real ? f32_from_orderable(ord) : __int_as_float(0x7f800000);
+            if (out_dist_i) out_dist_i[o] = real ? s32_from_orderable(ord) : 0x7fffffff;
+            if (out_id) out_id[o] = real ? (m & 0xFFFFFFFFull) : 0xFFFFFFFFFFFFFFFFull;
+            if (out_key) out_key[o] = m;
+        }
+    }
+}
+
 int launch_topk_merge(Ctx* ctx, const unsigned long long* keys, int L, long long nq, int k, long long list_stride,
                       float* out_dist_f, int* out_dist_i, unsigned long long* out_id, unsigned long long* out_key) {
     if (nq <= 0) return 0;
+    if (L >= 8 && (long long)L * k <= 512) {  // many short lists: minimum extraction from registers
+        const int wq = 4;
+        topk_merge_extract_kernel<<<(unsigned)((nq + wq - 1) / wq), wq * 32, 0, ctx->stream>>>(keys, L, nq, k, list_stride, out_dist_f,
+                                                                                             out_dist_i, out_id, out_key);
+        ctx->launches++;
+        B2_CUDA(cudaGetLastError());
+        return 0;
+    }
     int warps = 4;
     while (warps > 1 && (size_t)warps * L * k * 8 > 96 * 1024) warps >>= 1;
     const size_t smem = (size_t)warps * L * k * 8;

@@ -56,18 +56,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Insert `key` (smaller than the current k-th entry, distinct from every entry) into a THREAD-private ascending
-// list of k <= 32 keys in shared memory; returns the new k-th entry.
-__device__ __forceinline__ unsigned long long list_insert32(uint32_t L_addr, unsigned long long key, int k) {
-    int j = k - 1;
-    while (j > 0) {
-        const unsigned long long prev = lds64(L_addr + (uint32_t)(j - 1) * 8u);
-        if (prev < key) break;
-        sts64(L_addr + (uint32_t)j * 8u, prev);
-        j--;
+// THREAD-private top-k list of k <= 32 keys in shared memory, kept UNSORTED with its maximum tracked in registers
+// (tkey at slot tpos; KEY_MAX while a slot is still empty): an insertion overwrites the maximum and rescans the k
+// slots for the new one -- k independent loads instead of a dependent shift chain.  Sorted once at the end.
+__device__ __forceinline__ void list_replace_max(uint32_t L_addr, unsigned long long key, int k, unsigned long long& tkey, int& tpos) {
+    sts64(L_addr + (uint32_t)tpos * 8u, key);
+    unsigned long long mx = 0;
+    int mp = 0;
+#pragma unroll 4
+    for (int j = 0; j < k; j++) {
+        const unsigned long long v = lds64(L_addr + (uint32_t)j * 8u);
+        if (v >= mx) { mx = v; mp = j; }
     }
-    sts64(L_addr + (uint32_t)j * 8u, key);
-    return lds64(L_addr + (uint32_t)(k - 1) * 8u);
+    tkey = mx;
+    tpos = mp;
 }
 
 template <int TC_GROUPS>
@@ -75,22 +77,25 @@ __global__ void __launch_bounds__(TC_GROUPS * 128 + 32, 1)
 u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32][8][16] canonical B tiles
                   const int* __restrict__ xmeta,             // [tiles][2][256]: |x|^2 (padded rows: large), label rank
                   long long n, int D, const unsigned char* __restrict__ queries, long long nq, int n_slices, int k,
-                  unsigned long long* __restrict__ out_keys /*[slice * 2 + group][nq][k]*/) {
+                  const int* __restrict__ init_thr, int init_stride,  // optional: an upper bound on each query's k-th best distance
+                  int NS,                                              // B-tile ring stages (2..4, as many as shared memory allows)
+                  unsigned long long* __restrict__ out_keys /*[slice * groups + group][nq][k]*/) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t A_BYTES = (uint32_t)TC_M * D, B_BYTES = (uint32_t)TC_N * D;
     const uint32_t sA = s_base;
-    const uint32_t sB = sA + A_BYTES;                  // 2 stages
-    // row-meta ring (|x|^2 + label rank): 4 stages, because a tile's meta is read by its epilogue, which may
-    // still run after the tile's shared-memory B stage has been released (the MMA retires first); stage t&3
-    // is rewritten for tile t+4, whose load is issued only after the epilogue of tile t has signalled
-    const uint32_t sXN = sB + 2 * B_BYTES;             // 4 stages x (256 norms + 256 ranks)
-    const uint32_t sList = sXN + 4 * TC_META_BYTES;                  // [groups][128][k] keys
+    const uint32_t sB = sA + A_BYTES;                  // NS stages
+    // row-meta ring (|x|^2 + label rank): MS = NS + 2 stages, because a tile's meta is read by its epilogue, which
+    // may still run after the tile's shared-memory B stage has been released (the MMA retires first); stage t % MS
+    // is rewritten for tile t + MS, whose load is issued only after the epilogue of tile t has signalled
+    const int MS = NS + 2;
+    const uint32_t sXN = sB + (uint32_t)NS * B_BYTES;  // MS stages x (256 norms + 256 ranks)
+    const uint32_t sList = sXN + (uint32_t)MS * TC_META_BYTES;       // [groups][128][k] keys
     constexpr int TC_THREADS = TC_GROUPS * 128 + 32, TC_PRODUCER_WARP = TC_GROUPS * 4;
     const uint32_t sScratch = sList + (uint32_t)(TC_GROUPS * TC_M * k) * 8u;   // [warps][32 columns][32 lanes] words
     const uint32_t sQn = sScratch + TC_GROUPS * 4 * 32 * 32 * 4;             // [128] |q|^2
     const uint32_t bars = sQn + TC_M * 4;
-    const uint32_t b_full = bars, b_empty = bars + 16, acc_full = bars + 32, acc_empty = bars + 48, tmem_slot = bars + 64;
+    const uint32_t b_full = bars, b_empty = bars + 32, acc_full = bars + 64, acc_empty = bars + 80, tmem_slot = bars + 96;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long q0 = (long long)blockIdx.x * TC_M;
     const int slice = blockIdx.y;
@@ -104,9 +109,11 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         if (lane == 0) {
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < 4; i++) {
                 mbar_init(b_full + 8 * i, 1);
                 mbar_init(b_empty + 8 * i, 1);
+            }
+            for (int i = 0; i < 2; i++) {
                 mbar_init(acc_full + 8 * i, 1);
                 mbar_init(acc_empty + 8 * i, TC_GROUPS * 4);  // one arrival per epilogue warp
             }
@@ -144,29 +151,31 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
             // D = S32 (2<<4), A = B = unsigned 8-bit (0), K-major, N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t idesc = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
             auto load_tile = [&](int t) {
-                const int s = t & 1;
-                mbar_arrive_expect_tx(b_full + 8 * s, B_BYTES + TC_META_BYTES);
-                tma_load_1d(sB + (uint32_t)s * B_BYTES, xcan + (size_t)(t_lo + t) * B_BYTES, B_BYTES, b_full + 8 * s);
-                tma_load_1d(sXN + (uint32_t)(t & 3) * TC_META_BYTES, xmeta + (size_t)(t_lo + t) * 2 * TC_N, TC_META_BYTES, b_full + 8 * s);
+                const int sb = t % NS;
+                mbar_arrive_expect_tx(b_full + 8 * sb, B_BYTES + TC_META_BYTES);
+                tma_load_1d(sB + (uint32_t)sb * B_BYTES, xcan + (size_t)(t_lo + t) * B_BYTES, B_BYTES, b_full + 8 * sb);
+                tma_load_1d(sXN + (uint32_t)(t % MS) * TC_META_BYTES, xmeta + (size_t)(t_lo + t) * 2 * TC_N, TC_META_BYTES, b_full + 8 * sb);
             };
-            load_tile(0);
+            for (int t = 0; t < NS - 1 && t < T; t++) load_tile(t);  // NS-1 tiles in flight ahead of the MMA
             for (int t = 0; t < T; t++) {
-                const int s = t & 1, use = t >> 1;
-                if (t + 1 < T) {
-                    if (t + 1 >= 2) mbar_wait(b_empty + 8 * ((t + 1) & 1), (uint32_t)(((t + 1) >> 1) - 1) & 1u);  // MMAs of tile t-1 done
-                    load_tile(t + 1);
-                }
-                mbar_wait(b_full + 8 * s, (uint32_t)use & 1u);
+                const int sb = t % NS, s = t & 1, use = t >> 1;
+                mbar_wait(b_full + 8 * sb, (uint32_t)(t / NS) & 1u);
                 if (t >= 2) mbar_wait(acc_empty + 8 * s, (uint32_t)(use - 1) & 1u);  // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_base + (uint32_t)s * TC_N;
                 for (int ks = 0; ks < ksteps; ks++) {
                     const uint64_t da = tc_desc_kmajor(sA + (uint32_t)ks * 2 * A_LBO, A_LBO, SBO);
-                    const uint64_t db = tc_desc_kmajor(sB + (uint32_t)s * B_BYTES + (uint32_t)ks * 2 * B_LBO, B_LBO, SBO);
+                    const uint64_t db = tc_desc_kmajor(sB + (uint32_t)sb * B_BYTES + (uint32_t)ks * 2 * B_LBO, B_LBO, SBO);
                     umma_i8(acc, da, db, idesc, ks != 0);
                 }
-                tc_commit(b_empty + 8 * s);   // smem stage reusable once these MMAs retire
+                tc_commit(b_empty + 8 * sb);  // smem stage reusable once these MMAs retire
                 tc_commit(acc_full + 8 * s);  // accumulator ready for the epilogue
+                // refill: tile t+NS-1 goes to the stage tile t-1 used, once the MMAs of tile t-1 have retired
+                const int nxt = t + NS - 1;
+                if (nxt < T) {
+                    if (t >= 1) mbar_wait(b_empty + 8 * ((t - 1) % NS), (uint32_t)((t - 1) / NS) & 1u);
+                    load_tile(nxt);
+                }
             }
         }
     } else {
@@ -177,9 +186,12 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
         const uint32_t scratch = sScratch + (uint32_t)warp * (32 * 32 * 4) + (uint32_t)lane * 4u;
         int qn;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(qn) : "r"(sQn + (uint32_t)ql * 4u));
-        // tp = threshold on d' = |x|^2 - 2<q,x>  (dist - |q|^2); INT_MAX while the list is not full
+        // tp = threshold on d' = |x|^2 - 2<q,x>  (dist - |q|^2): the caller's bound (the k-th best distance over a
+        // sample of the rows: a row beyond it cannot be in the top-k; ties are kept), tightened by the own list once full
         int tp = 0x7fffffff;
+        if (init_thr != nullptr && qvalid) tp = __ldg(init_thr + (q0 + ql) * init_stride) - qn;
         unsigned long long tkey = KEY_MAX;
+        int tpos = 0;
         auto tld32 = [&](uint32_t (&r)[32], uint32_t taddr) {
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -225,8 +237,8 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rk) : "r"(meta_s + (uint32_t)(TC_N + c0 + i) * 4u));
                         const unsigned long long key = make_key(s32_orderable(dp + qn), rk);
                         if (key < tkey) {
-                            tkey = list_insert32(myList, key, k);
-                            if (tkey != KEY_MAX) tp = s32_from_orderable((uint32_t)(tkey >> 32)) - qn;  // list full: k-th distance
+                            list_replace_max(myList, key, k, tkey, tpos);
+                            if (tkey != KEY_MAX) tp = min(tp, s32_from_orderable((uint32_t)(tkey >> 32)) - qn);  // list full: k-th distance
                         }
                     }
                 }
@@ -238,7 +250,7 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
             mbar_wait(acc_full + 8 * s, (uint32_t)use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long row_base = (t_lo + t) * TC_N;
-            const uint32_t meta_s = sXN + (uint32_t)(t & 3) * TC_META_BYTES;
+            const uint32_t meta_s = sXN + (uint32_t)(t % MS) * TC_META_BYTES;
             const int cg = grp * (TC_N / TC_GROUPS);
             const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * TC_N + cg);
             uint32_t ra[32], rb[32];
@@ -256,9 +268,18 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * s);
         }
-        if (qvalid)
-            for (int j = 0; j < k; j++)
-                out_keys[((long long)(slice * TC_GROUPS + grp) * nq + q0 + ql) * k + j] = lds64(myList + (uint32_t)j * 8u);
+        if (qvalid) {  // emit the list ascending: rank of an entry = how many entries order before it
+            unsigned long long* out = out_keys + ((long long)(slice * TC_GROUPS + grp) * nq + q0 + ql) * k;
+            for (int j = 0; j < k; j++) {
+                const unsigned long long e = lds64(myList + (uint32_t)j * 8u);
+                int rank = 0;
+                for (int i = 0; i < k; i++) {
+                    const unsigned long long o = lds64(myList + (uint32_t)i * 8u);
+                    rank += (o < e || (o == e && i < j)) ? 1 : 0;  // empty slots (KEY_MAX) tie: index order
+                }
+                out[rank] = e;
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -297,14 +318,15 @@ __global__ void u8_rows_to_canonical_kernel(const unsigned char* __restrict__ ro
     }
 }
 
-static size_t tc_smem_bytes(int D, int k, int groups) {
-    return (size_t)TC_M * D + 2 * (size_t)TC_N * D + 4 * TC_META_BYTES + (size_t)groups * (TC_M * (size_t)k * 8 + 4 * 32 * 32 * 4) + TC_M * 4 + 128;
+static size_t tc_smem_bytes(int D, int k, int groups, int stages) {
+    return (size_t)TC_M * D + (size_t)stages * TC_N * D + (size_t)(stages + 2) * TC_META_BYTES +
+           (size_t)groups * (TC_M * (size_t)k * 8 + 4 * 32 * 32 * 4) + TC_M * 4 + 256;
 }
 // two epilogue groups when their lists and scratch fit beside the operand tiles, else one
-int u8_scan_tc_lists_per_slice(int D, int k) { return tc_smem_bytes(D, k, 2) <= (size_t)TC_MAX_SMEM ? 2 : 1; }
+int u8_scan_tc_lists_per_slice(int D, int k) { return tc_smem_bytes(D, k, 2, 2) <= (size_t)TC_MAX_SMEM ? 2 : 1; }
 
 bool u8_scan_tc_supported(int D, int k) {
-    return D % 32 == 0 && D >= 32 && D <= 256 && k >= 1 && k <= TC_KP && tc_smem_bytes(D, k, 1) <= (size_t)TC_MAX_SMEM;
+    return D % 32 == 0 && D >= 32 && D <= 256 && k >= 1 && k <= TC_KP && tc_smem_bytes(D, k, 1, 2) <= (size_t)TC_MAX_SMEM;
 }
 
 int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint32_t* rank, long long n, int D, unsigned char* xcan,
@@ -326,18 +348,20 @@ int u8_scan_tc_slices(int sm_count, long long nq, long long n) {
 }
 
 int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, int D, const unsigned char* queries,
-                      long long nq, int n_slices, int k, unsigned long long* out_keys) {
+                      long long nq, int n_slices, int k, const int* init_thr, int init_stride, unsigned long long* out_keys) {
     if (nq <= 0) return 0;
     if (!u8_scan_tc_supported(D, k)) B2_FAIL(-4, "u8 tensor-core scan: needs D % 32 == 0, D <= 256, k <= 32");
     const int groups = u8_scan_tc_lists_per_slice(D, k);
-    const size_t smem = tc_smem_bytes(D, k, groups);
+    int stages = 4;  // B-tile ring: as deep as shared memory allows (hides the TMA latency behind two epilogues and more)
+    while (stages > 2 && tc_smem_bytes(D, k, groups, stages) > (size_t)TC_MAX_SMEM) stages--;
+    const size_t smem = tc_smem_bytes(D, k, groups, stages);
     dim3 grid((unsigned)((nq + TC_M - 1) / TC_M), (unsigned)n_slices);
     if (groups == 2) {
         B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        u8_scan_tc_kernel<2><<<grid, 2 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, out_keys);
+        u8_scan_tc_kernel<2><<<grid, 2 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, init_thr, init_stride, stages, out_keys);
     } else {
         B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        u8_scan_tc_kernel<1><<<grid, 1 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, out_keys);
+        u8_scan_tc_kernel<1><<<grid, 1 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, init_thr, init_stride, stages, out_keys);
     }
     ctx->launches++;
     B2_CUDA(cudaGetLastError());

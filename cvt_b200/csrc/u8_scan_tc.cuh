@@ -11,8 +11,10 @@ int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint3
                                 int* xmeta, long long n_pad);
 int u8_scan_tc_slices(int sm_count, long long nq, long long n);
 int u8_scan_tc_lists_per_slice(int D, int k);
-// out_keys [n_slices * u8_scan_tc_lists_per_slice(D, k)][nq][k]; ids in the keys are label ranks
+// out_keys [n_slices * u8_scan_tc_lists_per_slice(D, k)][nq][k]; ids in the keys are label ranks.
+// init_thr (may be NULL): init_thr[q * init_stride] = an upper bound on query q's k-th best distance, e.g. the k-th
+// best over a prefix of the rows -- rows beyond it are dropped (ties kept), so lists may come back shorter than k.
 int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, int D, const unsigned char* queries,
-                      long long nq, int n_slices, int k, unsigned long long* out_keys);
+                      long long nq, int n_slices, int k, const int* init_thr, int init_stride, unsigned long long* out_keys);
 
 }  // namespace b200nn

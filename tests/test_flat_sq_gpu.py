@@ -175,7 +175,9 @@ def test_sq_roundtrip_property_at_size(ctx):
 
 
 @pytest.mark.parametrize("D,n,nq,k,hi", [(128, 33_333, 130, 10, 256), (32, 1000, 5, 1, 256), (64, 5000, 300, 32, 3), (256, 2049, 129, 7, 256),
-                                          (128, 200, 17, 32, 2)])
+                                          (128, 200, 17, 32, 2), (256, 3000, 40, 32, 256),
+                                          # >= 262144 rows: the sample pass seeds the thresholds; tie-heavy so that rows AT the bound matter
+                                          (32, 300_001, 70, 10, 3), (64, 270_000, 33, 32, 256)])
 def test_u8_tensor_core_scan_vs_oracle_and_dp4a(ctx, D, n, nq, k, hi):
     """cfg2 path: tcgen05 kind::i8 GEMM + fused top-k == oracle (L2SqrI + (dist,label) heap rule) == dp4a kernel,
     on ragged sizes and tie-heavy data (hi=2,3: tiny alphabets -> masses of equal distances)."""
