@@ -235,7 +235,10 @@ __global__ void lut_build_scan_kernel(const float* __restrict__ q, long long nq,
     }
     __syncthreads();
     float* out = lut_scan + qg * 32768;
-    for (int e = threadIdx.x; e < 32768; e += blockDim.x) {
+    // blockIdx.y = which slice of the group's 32768 entries: more CTAs than query groups, so that a small batch
+    // (one rank's chunk of a sharded batch) still fills the machine
+    const int e_per = 32768 / (int)gridDim.y;
+    for (int e = (int)blockIdx.y * e_per + threadIdx.x; e < ((int)blockIdx.y + 1) * e_per; e += blockDim.x) {
         const int lane = e & 31, msel = (e >> 5) & 1, j = (e >> 6) & 255, pair = e >> 14;
         const int h = lane / QW, ql = lane - h * QW;
         const int m = 4 * h + 2 * pair + msel;
@@ -1010,7 +1013,10 @@ static int lut_scan_dispatch(Ctx* ctx, const float* q, long long nq, int D, cons
                              float* lut_scan) {
     constexpr int QW = 32 / G, M = 4 * G;
     const int ds = D / M;
-    const unsigned grid = (unsigned)((nq + QW - 1) / QW);
+    const unsigned qgroups = (unsigned)((nq + QW - 1) / QW);
+    unsigned parts = 1;  // entry slices per query group: aim at >= 4 CTAs per SM
+    while (parts < 8 && (unsigned long long)qgroups * parts < 4ull * ctx->sm_count) parts *= 2;
+    const dim3 grid(qgroups, parts);
     const size_t smem = (size_t)QW * (D + 4) * sizeof(float);
 #define B2_LS(DS_)                                                                                                  \
     case DS_:                                                                                                       \
