@@ -28,6 +28,7 @@ SYMBOLS = [
     "b200nn_pq_save_index", "b200nn_pq_load_index", "b200nn_pq_last_timing", "b200nn_pq_scan_bytes",
     "b200nn_sq_create", "b200nn_sq_destroy", "b200nn_sq_train_minmax", "b200nn_sq_encode", "b200nn_sq_decode",
     "b200nn_sq_encode_dev",
+    "b200nn_proj_create", "b200nn_proj_destroy", "b200nn_proj_apply", "b200nn_proj_apply_dev", "b200nn_rootsift", "b200nn_rootsift_dev",
 ]
 
 _lib = None
@@ -393,3 +394,44 @@ class SQ:
         x = np.empty(codes.shape, dtype=np.float32)
         _check(load().b200nn_sq_decode(self.h, _vp(codes), C.c_size_t(codes.shape[0]), C.c_int(int(faiss_float)), _vp(x)), "sq_decode")
         return x
+
+
+class Projection:
+    """cvtk::PCAUtils drop-in surface (pca_train_project/pca_online/pca_utils.h): reduceDim = PCA project + L2 normalise."""
+
+    def __init__(self, ctx: Context, vectors, mean=None):
+        self.ctx = ctx
+        vectors = _f32(vectors)
+        self.N, self.K = vectors.shape
+        mean_a = None if mean is None else _f32(mean).reshape(-1)
+        self.h = C.c_void_p()
+        _check(load().b200nn_proj_create(ctx.h, C.c_int(self.K), C.c_int(self.N), _vp(mean_a), _vp(vectors), C.byref(self.h)), "proj_create")
+        ctx._adopt(self)
+
+    def close(self):
+        if self.h:
+            load().b200nn_proj_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reduce_dim(self, x, l2norm=True):
+        x = _f32(x)
+        y = np.empty((x.shape[0], self.N), dtype=np.float32)
+        _check(load().b200nn_proj_apply(self.h, _vp(x), C.c_size_t(x.shape[0]), C.c_int(int(l2norm)), _vp(y)), "proj_apply")
+        return y
+
+    def reduce_dim_dev(self, x_dev_ptr: int, n: int, y_dev_ptr: int, l2norm=True):
+        _check(load().b200nn_proj_apply_dev(self.h, C.c_void_p(x_dev_ptr), C.c_size_t(n), C.c_int(int(l2norm)), C.c_void_p(y_dev_ptr)),
+               "proj_apply_dev")
+
+
+def rootsift(ctx: Context, x, eps: float = 1e-7):
+    """siftsIDX::rootSift on the device; returns a new array (the reference works in place)."""
+    y = _f32(x).copy()
+    _check(load().b200nn_rootsift(ctx.h, _vp(y), C.c_size_t(y.shape[0]), C.c_int(y.shape[1]), C.c_float(eps)), "rootsift")
+    return y

@@ -1,3 +1,8 @@
+// rotate_gemm.cu -- dense projections Y[n,N] = (X[n,K] - mean) * V^T on the tensor cores.  Two users:
+//   a1  the OPQ rotation as a dense matrix (K = N = D, no mean), bit-identical to the reference's permutation;
+//   f-3 the PCA front end cvtk::PCAUtils::reduceDim (pca_train_project/pca_online/pca_utils.cc:25-35):
+//       cv::PCA::project = (x - mean) * eigenvectors^T, then the per-row L2 normalisation, fused in the epilogue.
+// Written for a1 first, hence the name:
 // rotate_gemm.cu -- a1 as a dense rotation: Y[n,D] = X[n,D] * R^T on the 5th-generation tensor
 // cores (tcgen05.mma kind::tf32, accumulators in TMEM), at ~fp32 accuracy through an error-free
 // split of both operands ("3xTF32"):
@@ -54,10 +59,13 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
 }
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-template <int NB>
+// MODE 0: plain store.  MODE 1 (needs N == NB, one CTA owns whole output rows): the reference's row normalisation
+//   normMat = row * row.t() (OpenCV gemm: float products accumulated in double, stored as float);
+//   denomv = max(1e-12, (double)sqrt(normMat)) as float; row /= denomv        (pca_utils.cc:28-34)
+template <int NB, int MODE>
 __global__ void __launch_bounds__(RG_THREADS, 1)
-rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int D, const float* __restrict__ bplanes,
-                          float* __restrict__ y) {
+rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N, const float* __restrict__ mean,
+                          const float* __restrict__ bplanes, float* __restrict__ y) {
     constexpr uint32_t A_PLANE = RG_M * RG_KC * 4;       // 16 KB
     constexpr uint32_t B_PLANE = NB * RG_KC * 4;         // 8 / 16 KB
     constexpr uint32_t A_LBO = RG_M * 16, B_LBO = NB * 16, SBO = 128;
@@ -70,7 +78,7 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int D, const
     const int tid = threadIdx.x, warp = tid >> 5;
     const int nblk = blockIdx.x;                           // output column block (fastest: shares X rows in L2)
     const long long tile = blockIdx.y;
-    const int nchunks = D / RG_KC;
+    const int nchunks = K / RG_KC;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)NB) : "memory");
@@ -93,7 +101,7 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int D, const
 
     const long long row = tile * RG_M + tid;
     const bool valid = row < n;
-    const float* xrow = x + row * D;
+    const float* xrow = x + row * K;
     const uint32_t a_row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
 
     for (int kc = 0; kc < nchunks; kc++) {
@@ -109,6 +117,10 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int D, const
         for (int c = 0; c < RG_KC / 4; c++) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) v = __ldg(reinterpret_cast<const float4*>(xrow + kc * RG_KC + c * 4));
+            if (mean != nullptr) {  // cv::PCA::project subtracts the mean first (one fp32 rounding), then multiplies
+                const float4 mv = __ldg(reinterpret_cast<const float4*>(mean + kc * RG_KC + c * 4));
+                v.x = __fsub_rn(v.x, mv.x); v.y = __fsub_rn(v.y, mv.y); v.z = __fsub_rn(v.z, mv.z); v.w = __fsub_rn(v.w, mv.w);
+            }
             const float h0 = tf32_trunc(v.x), h1 = tf32_trunc(v.y), h2 = tf32_trunc(v.z), h3 = tf32_trunc(v.w);
             const float r0 = __fsub_rn(v.x, h0), r1 = __fsub_rn(v.y, h1), r2 = __fsub_rn(v.z, h2), r3 = __fsub_rn(v.w, h3);
             const float m0 = tf32_trunc(r0), m1 = tf32_trunc(r1), m2 = tf32_trunc(r2), m3 = tf32_trunc(r3);
@@ -145,10 +157,8 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int D, const
     // ---- epilogue: TMEM -> registers -> global ----
     mbar_wait(accum_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* yrow = y + row * D + (size_t)nblk * NB;
-#pragma unroll
-    for (int c0 = 0; c0 < NB; c0 += 32) {
-        uint32_t r[32];
+    float* yrow = y + row * N + (size_t)nblk * NB;
+    auto tld32 = [&](uint32_t (&r)[32], int c0) {
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -159,11 +169,34 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int D, const
               "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    };
+    float denomv = 1.0f;
+    if (MODE == 1) {  // thread = row: sum of squares over the row's N outputs, in column order, accumulated in double
+        double ss = 0.0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NB; c0 += 32) {
+            uint32_t r[32];
+            tld32(r, c0);
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const double v = (double)__uint_as_float(r[i]);
+                ss = __dadd_rn(ss, __dmul_rn(v, v));
+            }
+        }
+        const double d = (double)__fsqrt_rn((float)ss);
+        denomv = (float)(d > 1e-12 ? d : 1e-12);
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < NB; c0 += 32) {
+        uint32_t r[32];
+        tld32(r, c0);
         if (valid) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(yrow + c0 + i) =
-                    make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            for (int i = 0; i < 32; i += 4) {
+                float4 o = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                if (MODE == 1) { o.x = __fdiv_rn(o.x, denomv); o.y = __fdiv_rn(o.y, denomv); o.z = __fdiv_rn(o.z, denomv); o.w = __fdiv_rn(o.w, denomv); }
+                *reinterpret_cast<float4*>(yrow + c0 + i) = o;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -176,11 +209,18 @@ int rotate_gemm_nblock(int D) { return (D % 128 == 0) ? 128 : 64; }
 
 bool rotate_gemm_supported(int D) { return D >= 64 && D % 64 == 0; }
 
-// R [D,D] row-major (y = R x) -> two TF32-exact parts in the canonical K-major core-matrix order,
+// output-column block of a projection to N columns: with the fused row normalisation one CTA must own whole rows
+int proj_gemm_nblock(int N, bool l2norm) {
+    if (l2norm) return (N == 64 || N == 128 || N == 256) ? N : 0;
+    return (N % 64 == 0 && N >= 64) ? ((N % 128 == 0) ? 128 : 64) : 0;
+}
+bool proj_gemm_supported(int K, int N, bool l2norm) { return K >= 32 && K % 32 == 0 && proj_gemm_nblock(N, l2norm) != 0; }
+
+// V [N,K] row-major (y = V x) -> two TF32-exact parts in the canonical K-major core-matrix order,
 // one contiguous block per (output block, K chunk): [nblk][kc][part][ (k/4) | (n/8) | n%8 | k%4 ]
-void rotate_gemm_pack_R(const float* R, int D, std::vector<float>& out) {
-    const int NB = rotate_gemm_nblock(D), nblocks = D / NB, nchunks = D / RG_KC;
-    out.assign((size_t)D * D * 2, 0.0f);
+void proj_gemm_pack(const float* V, int N, int K, int NB, std::vector<float>& out) {
+    const int nblocks = N / NB, nchunks = K / RG_KC;
+    out.assign((size_t)N * K * 2, 0.0f);
     auto trunc = [](float v) {
         union { float f; uint32_t u; } c;
         c.f = v;
@@ -192,7 +232,7 @@ void rotate_gemm_pack_R(const float* R, int D, std::vector<float>& out) {
             float* blk = out.data() + ((size_t)nb * nchunks + kc) * (2 * NB * RG_KC);
             for (int nl = 0; nl < NB; nl++)
                 for (int kl = 0; kl < RG_KC; kl++) {
-                    const float v = R[(size_t)(nb * NB + nl) * D + kc * RG_KC + kl];
+                    const float v = V[(size_t)(nb * NB + nl) * K + kc * RG_KC + kl];
                     const float r0 = trunc(v), r1 = trunc(v - r0);
                     const size_t off = (size_t)(kl / 4) * (NB * 4) + (size_t)(nl / 8) * 32 + (nl % 8) * 4 + (kl % 4);
                     blk[off] = r0;
@@ -201,29 +241,42 @@ void rotate_gemm_pack_R(const float* R, int D, std::vector<float>& out) {
         }
 }
 
-int launch_rotate_gemm(Ctx* ctx, const float* x, long long n, int D, const float* bplanes, float* y) {
-    if (n <= 0) return 0;
-    if (!rotate_gemm_supported(D)) B2_FAIL(-4, "dense rotation needs D % 64 == 0");
-    const int NB = rotate_gemm_nblock(D);
+void rotate_gemm_pack_R(const float* R, int D, std::vector<float>& out) { proj_gemm_pack(R, D, D, rotate_gemm_nblock(D), out); }
+
+template <int NB, int MODE>
+static int proj_launch(Ctx* ctx, const float* x, long long n, int K, int N, const float* mean, const float* bplanes, float* y) {
     const size_t smem = 2 * 3 * (size_t)RG_M * RG_KC * 4 + 2 * 2 * (size_t)NB * RG_KC * 4 + 64;
+    B2_CUDA(cudaFuncSetAttribute(rotate_gemm_tf32x3_kernel<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long n_tiles = (n + RG_M - 1) / RG_M;
-    // gridDim.y limit is 65535: fold the row tiles into several launches
-    const long long max_tiles = 65535;
+    const long long max_tiles = 65535;  // gridDim.y limit: fold the row tiles into several launches
     for (long long t0 = 0; t0 < n_tiles; t0 += max_tiles) {
         const long long tiles = std::min<long long>(max_tiles, n_tiles - t0);
         const long long rows0 = t0 * RG_M, rows = std::min<long long>(n - rows0, tiles * RG_M);
-        dim3 g((unsigned)(D / NB), (unsigned)tiles);
-        if (NB == 128) {
-            B2_CUDA(cudaFuncSetAttribute(rotate_gemm_tf32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            rotate_gemm_tf32x3_kernel<128><<<g, RG_THREADS, smem, ctx->stream>>>(x + rows0 * D, rows, D, bplanes, y + rows0 * D);
-        } else {
-            B2_CUDA(cudaFuncSetAttribute(rotate_gemm_tf32x3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            rotate_gemm_tf32x3_kernel<64><<<g, RG_THREADS, smem, ctx->stream>>>(x + rows0 * D, rows, D, bplanes, y + rows0 * D);
-        }
+        dim3 g((unsigned)(N / NB), (unsigned)tiles);
+        rotate_gemm_tf32x3_kernel<NB, MODE><<<g, RG_THREADS, smem, ctx->stream>>>(x + rows0 * K, rows, K, N, mean, bplanes, y + rows0 * N);
         ctx->launches++;
     }
     B2_CUDA(cudaGetLastError());
     return 0;
+}
+
+int launch_proj_gemm(Ctx* ctx, const float* x, long long n, int K, int N, const float* mean, const float* bplanes, bool l2norm, float* y) {
+    if (n <= 0) return 0;
+    if (!proj_gemm_supported(K, N, l2norm)) B2_FAIL(-4, "projection GEMM needs K % 32 == 0 and N % 64 == 0 (N in {64, 128, 256} with the fused L2 normalisation)");
+    const int NB = proj_gemm_nblock(N, l2norm);
+    if (l2norm) {
+        if (NB == 64) return proj_launch<64, 1>(ctx, x, n, K, N, mean, bplanes, y);
+        if (NB == 128) return proj_launch<128, 1>(ctx, x, n, K, N, mean, bplanes, y);
+        return proj_launch<256, 1>(ctx, x, n, K, N, mean, bplanes, y);
+    }
+    if (NB == 128) return proj_launch<128, 0>(ctx, x, n, K, N, mean, bplanes, y);
+    return proj_launch<64, 0>(ctx, x, n, K, N, mean, bplanes, y);
+}
+
+int launch_rotate_gemm(Ctx* ctx, const float* x, long long n, int D, const float* bplanes, float* y) {
+    if (n <= 0) return 0;
+    if (!rotate_gemm_supported(D)) B2_FAIL(-4, "dense rotation needs D % 64 == 0");
+    return launch_proj_gemm(ctx, x, n, D, D, nullptr, bplanes, false, y);
 }
 
 }  // namespace b200nn

@@ -37,6 +37,7 @@ typedef struct b200nn_ctx* b200nn_ctx_t;
 typedef struct b200nn_flat* b200nn_flat_t;
 typedef struct b200nn_pq* b200nn_pq_t;
 typedef struct b200nn_sq* b200nn_sq_t;
+typedef struct b200nn_proj* b200nn_proj_t;
 
 /* ---- context ---------------------------------------------------------------------------- */
 const char* b200nn_last_error(void);
@@ -152,6 +153,22 @@ int b200nn_sq_encode(b200nn_sq_t sq, float* x, size_t n, int l2norm, uint8_t* co
  * variant 1 = faiss 1.5.3's all-float decode (reached via Int8Decode(uint8_t*)/Int8DecodeFaiss). */
 int b200nn_sq_decode(b200nn_sq_t sq, const uint8_t* codes, size_t n, int faiss_float_variant, float* x);
 int b200nn_sq_encode_dev(b200nn_sq_t sq, float* x_dev, size_t n, int l2norm, uint8_t* codes_dev);
+
+/* ---- front end (the steps that produce the vectors fed to the path) --------------------------------
+ * cvtk::PCAUtils (pca_train_project/pca_online/pca_utils.h:10-27, pca_utils.cc:16-35): loadModel reads cv::PCA's
+ * `mean` [K_in] and `vectors` (eigenvectors, row-major [N_out, K_in]); reduceDim = cv::PCA::project, i.e.
+ * y = (x - mean) * vectors^T, followed (l2norm != 0) by the per-row L2 normalisation of pca_utils.cc:28-34.
+ * Runs as a tcgen05 split-TF32 GEMM (fp32-level accuracy; the reference's OpenCV gemm accumulates in double):
+ * K_in % 32 == 0, N_out % 64 == 0, and N_out in {64, 128, 256} when l2norm is requested. */
+int b200nn_proj_create(b200nn_ctx_t ctx, int K_in, int N_out, const float* mean /*[K_in] or NULL*/, const float* vectors,
+                       b200nn_proj_t* out);
+void b200nn_proj_destroy(b200nn_proj_t p);
+int b200nn_proj_apply(b200nn_proj_t p, const float* x /*[n,K_in]*/, size_t n, int l2norm, float* y /*[n,N_out]*/);
+int b200nn_proj_apply_dev(b200nn_proj_t p, const float* x_dev, size_t n, int l2norm, float* y_dev);
+/* siftsIDX::rootSift (hnsw_sifts_retrieval/siftsIndex.cpp:54-71, eps = 1e-7 there), in place over n rows of d floats:
+ * abs -> / (L1 + eps) -> sqrt -> cv::normalize(NORM_L2); both sums accumulate in double, in column order. */
+int b200nn_rootsift(b200nn_ctx_t ctx, float* x, size_t n, int d, float eps);
+int b200nn_rootsift_dev(b200nn_ctx_t ctx, float* x_dev, size_t n, int d, float eps);
 
 #ifdef __cplusplus
 }

@@ -405,3 +405,54 @@ ORC_API void orc_sq_train_minmax(const float* x, int64_t n, int d, float* vmin, 
         vdiff[j] = hi - lo;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * front end: the steps that PRODUCE the vectors fed to the path.
+ * Both call into OpenCV (cv::PCA::project, cv::reduce, cv::normalize), an un-vendored dependency:
+ * pinned against cv2 4.13 (Python, this container) outputs under tests/golden/ -- OpenCV's gemm
+ * accumulates float products in double (GEMMSingleMul<float,double>), which is restated here; its SIMD
+ * reduction orders are not, hence a tolerance (a few ulp) instead of bit equality at this boundary.
+ * ---------------------------------------------------------------------------------------- */
+
+/* cvtk::PCAUtils::reduceDim, pca_train_project/pca_online/pca_utils.cc:25-35:
+ *   pca_.project(mat, reduceMat)      == (x - mean) * eigenvectors^T  (cv::PCA::project: subtract, then gemm)
+ *   per row: normMat = row * row.t(); denomv = max(1e-12, (double)sqrt(normMat.at<float>(0,0))); row /= denomv
+ * vectors = cv::PCA::eigenvectors, row-major [N][K]; mean [K]. */
+ORC_API void orc_pca_project(const float* x, int64_t n, int K, const float* mean, const float* vectors, int N, int l2norm, float* y) {
+    float* t = (float*)malloc(sizeof(float) * (size_t)K);
+    for (int64_t r = 0; r < n; r++) {
+        for (int k = 0; k < K; k++) t[k] = mean ? x[r * K + k] - mean[k] : x[r * K + k];
+        float* yr = y + r * N;
+        for (int j = 0; j < N; j++) {
+            double acc = 0.0;
+            for (int k = 0; k < K; k++) acc += (double)t[k] * (double)vectors[(int64_t)j * K + k];
+            yr[j] = (float)acc;
+        }
+        if (l2norm) {
+            double s = 0.0;
+            for (int j = 0; j < N; j++) s += (double)yr[j] * (double)yr[j];
+            const float nrm2 = (float)s;
+            const double d = (double)sqrtf(nrm2);
+            const float denomv = (float)(d > 1e-12 ? d : 1e-12);
+            for (int j = 0; j < N; j++) yr[j] = yr[j] / denomv;
+        }
+    }
+    free(t);
+}
+
+/* siftsIDX::rootSift, hnsw_sifts_retrieval/siftsIndex.cpp:54-71 (same code makeSIFTs.cpp:79-95), eps = 1e-7:
+ *   d = abs(d); sums = reduce(d, SUM over columns, CV_32F); d = sqrt(d / (sums + eps)); normalize(row, NORM_L2)
+ * cv::normalize(NORM_L2, alpha = 1): scale = 1 / norm(row) with the norm accumulated in double, row *= scale. */
+ORC_API void orc_rootsift(float* x, int64_t n, int d, float eps) {
+    for (int64_t r = 0; r < n; r++) {
+        float* v = x + r * d;
+        double sum = 0.0;
+        for (int j = 0; j < d; j++) { v[j] = fabsf(v[j]); sum += (double)v[j]; }
+        const float sums = (float)sum;
+        double s2 = 0.0;
+        for (int j = 0; j < d; j++) { v[j] = sqrtf(v[j] / (sums + eps)); s2 += (double)v[j] * (double)v[j]; }
+        const double nrm = sqrt(s2);
+        const double scale = nrm > 2.220446049250313e-16 ? 1.0 / nrm : 0.0;  /* cv::normalize: DBL_EPSILON guard */
+        for (int j = 0; j < d; j++) v[j] = (float)((double)v[j] * scale);
+    }
+}

@@ -196,6 +196,24 @@ def sq_train_minmax(x):
     return vmin, vdiff
 
 
+# ---------------------------------------------------------------------------- front end (f-3)
+def pca_project(x, mean, vectors, l2norm=True):
+    """cvtk::PCAUtils::reduceDim (pca_train_project/pca_online/pca_utils.cc:25-35)."""
+    x, vectors = _f32(x), _f32(vectors)
+    mean_a = None if mean is None else _f32(mean).reshape(-1)
+    y = np.empty((x.shape[0], vectors.shape[0]), dtype=np.float32)
+    lib().orc_pca_project(_p(x), C.c_int64(x.shape[0]), C.c_int(x.shape[1]), None if mean_a is None else _p(mean_a), _p(vectors),
+                          C.c_int(vectors.shape[0]), C.c_int(int(l2norm)), _p(y))
+    return y
+
+
+def rootsift(x, eps=1e-7):
+    """siftsIDX::rootSift (hnsw_sifts_retrieval/siftsIndex.cpp:54-71); returns a new array."""
+    y = _f32(x).copy()
+    lib().orc_rootsift(_p(y), C.c_int64(y.shape[0]), C.c_int(y.shape[1]), C.c_float(eps))
+    return y
+
+
 # ---------------------------------------------------------------------------- compiled reference
 def parse_ref_opq(path: str) -> dict:
     b = open(path, "rb").read()

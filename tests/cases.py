@@ -130,3 +130,23 @@ def cli_case():
     db_ids = [f"img_{i:06d}" for i in range(c["n"])]
     q_ids = [f"query_{i:03d}" for i in range(c["nq"])]
     return dict(db=c["x"], q=c["q"], db_ids=db_ids, q_ids=q_ids)
+
+
+# ------------------------------------------------------------------------------- front end (f-3)
+def frontend_pca_inputs(K: int = 1024, n: int = 96):
+    """ReLU-sparse "CNN pool feature" rows (what pca_train_project reduces), plus edge rows: the all-zero row and a row
+    equal to nothing-but-noise at 1e-3 scale (small norms exercise the max(1e-12, norm) guard's neighbourhood)."""
+    rng = np.random.Generator(np.random.PCG64(0xF3000 + K))
+    x = np.maximum(rng.standard_normal((n, K), dtype=np.float32) * np.float32(0.8) + np.float32(0.2), 0).astype(np.float32)
+    x[1] = 0
+    x[2] *= np.float32(1e-3)
+    return x
+
+
+def frontend_sift_inputs(n: int = 80, d: int = 128):
+    """SIFT-like integer-valued descriptors 0..255 (some negated: rootSift takes abs first), one all-zero row."""
+    rng = np.random.Generator(np.random.PCG64(0x51F7))
+    v = np.minimum(np.floor(np.abs(rng.standard_normal((n, d), dtype=np.float32)) * np.float32(45.0)), np.float32(255.0))
+    v[::7] *= np.float32(-1.0)
+    v[3] = 0
+    return v.astype(np.float32)

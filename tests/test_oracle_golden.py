@@ -145,3 +145,20 @@ def test_reference_binary_agrees_with_golden(tmp_path):
     r = orc.run_ref_opq(os.path.join(G, "opq_shipped_k256.model"), gdb, gq, nk=3, topk=5, per_row=False)
     assert np.array_equal(r["codes"], gold["codes"])
     assert np.array_equal(_bits(r["match"]), _bits(gold["match"]))
+
+
+def test_frontend_restatement_equals_cv2_golden():
+    """f-3: the restatements of cvtk::PCAUtils::reduceDim and siftsIDX::rootSift against the committed cv2 outputs
+    (oracle/gen_golden_frontend.py; cv2 is the dependency the reference calls, the model is the reference's own)."""
+    gp = np.load(os.path.join(cases.GOLDEN, "frontend_pca.npz"))
+    x = cases.frontend_pca_inputs(1024)
+    assert str(gp["input_sha"]) == cases.sha(x)
+    y = orc.pca_project(x, gp["mean"], gp["vectors"], True)
+    assert np.array_equal(y.view(np.uint32), gp["y"].view(np.uint32))
+    assert np.allclose(np.linalg.norm(y, axis=1), 1.0, atol=1e-6)
+    gr = np.load(os.path.join(cases.GOLDEN, "frontend_rootsift.npz"))
+    d = cases.frontend_sift_inputs()
+    assert str(gr["input_sha"]) == cases.sha(d)
+    r = orc.rootsift(d)
+    assert np.array_equal(r.view(np.uint32), gr["y"].view(np.uint32))
+    assert np.all(r[3] == 0)  # the all-zero descriptor stays zero (cv::normalize's epsilon guard)
