@@ -80,17 +80,31 @@ def build_tools(force: bool = False, verbose: bool = False):
         if force or _newer([s, LIB] + hdrs, o):
             _run([gxx, "-O2", "-std=c++14", "-I", os.path.join(ROOT, "include"), s, "-o", o, "-L", LIBDIR, "-lb200nn",
                   "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../../cvt_b200/lib"], o + ".log")
-    # the reference's OWN brute-force CLI, unmodified, compiled in place against the forwarding
-    # headers and linked with libb200nn: the drop-in proof (only where /root/reference exists; the
-    # binary then travels with the snapshot)
-    ref_src = "/root/reference/brute_force_search/src/brute_force.cpp"
-    o = os.path.join(bdir, "ref_brute_force_on_b200nn")
-    if os.path.exists(ref_src):
-        if force or _newer([ref_src, LIB] + hdrs, o):
-            _run([gxx, "-O2", "-std=c++11", "-fno-operator-names", "-I", os.path.join(ROOT, "include", "b200nn", "compat"),
-                  ref_src, "-o", o, "-L", LIBDIR, "-lb200nn", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../../cvt_b200/lib"], o + ".log")
-    if os.path.exists(o):
-        outs.append(o)
+    # the reference's OWN mains, unmodified, compiled in place against the forwarding headers and linked with
+    # libb200nn: the drop-in proof (only where /root/reference exists; the binaries then travel with the snapshot).
+    # A quoted #include resolves next to the including file FIRST, so compiling the reference file by path would
+    # silently pick up the reference's own CPU headers sitting beside it; the source is therefore piped to the
+    # compiler on stdin (the "current directory" of the translation unit is then a neutral one) and the result is
+    # checked to import the C ABI.
+    compat = os.path.join(ROOT, "include", "b200nn", "compat")
+    for ref_src, name, std, need in (
+            ("/root/reference/brute_force_search/src/brute_force.cpp", "ref_brute_force_on_b200nn", "c++11", "b200nn_flat_search"),
+            ("/root/reference/opq/train_codebook/train_PQ.cpp", "ref_train_PQ_on_b200nn", "c++11", "b200nn_kmeans")):
+        o = os.path.join(bdir, name)
+        if os.path.exists(ref_src) and (force or _newer([ref_src, LIB] + hdrs, o)):
+            with open(ref_src, "rb") as src:
+                r = subprocess.run([gxx, "-O2", "-std=" + std, "-fno-operator-names", "-I", compat, "-x", "c++", "-", "-o", o, "-L", LIBDIR,
+                                    "-lb200nn", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../../cvt_b200/lib"],
+                                   stdin=src, cwd=OBJDIR, capture_output=True, text=True)
+            open(o + ".log", "w").write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"build failed: {name} from {ref_src}")
+            if need.encode() not in open(o, "rb").read():
+                os.remove(o)
+                raise RuntimeError(f"{name} does not import {need}: it was not compiled against the drop-in headers")
+        if os.path.exists(o):
+            outs.append(o)
     return outs
 
 

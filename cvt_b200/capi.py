@@ -29,6 +29,7 @@ SYMBOLS = [
     "b200nn_sq_create", "b200nn_sq_destroy", "b200nn_sq_train_minmax", "b200nn_sq_encode", "b200nn_sq_decode",
     "b200nn_sq_encode_dev",
     "b200nn_proj_create", "b200nn_proj_destroy", "b200nn_proj_apply", "b200nn_proj_apply_dev", "b200nn_rootsift", "b200nn_rootsift_dev",
+    "b200nn_kmeans", "b200nn_kmeans_init_rows", "b200nn_kmeans_plan_update", "b200nn_pq_train", "b200nn_pq_write_model",
 ]
 
 _lib = None
@@ -435,3 +436,61 @@ def rootsift(ctx: Context, x, eps: float = 1e-7):
     y = _f32(x).copy()
     _check(load().b200nn_rootsift(ctx.h, _vp(y), C.c_size_t(y.shape[0]), C.c_int(y.shape[1]), C.c_float(eps)), "rootsift")
     return y
+
+
+def kmeans(ctx: Context, x, k: int, max_iter: int = 0, seed: int = 0):
+    """Deterministic Lloyd k-means on the device (replaces yael's kmeans, train_PQ_codebook.cpp:164,229).
+    Returns (centroids [k,d], assign [n], dist [n], iterations, mse)."""
+    x = _f32(x)
+    n, d = x.shape
+    c = np.empty((k, d), dtype=np.float32)
+    a = np.empty(n, dtype=np.int32)
+    dist = np.empty(n, dtype=np.float32)
+    it = C.c_int(0)
+    mse = C.c_double(0.0)
+    _check(load().b200nn_kmeans(ctx.h, _vp(x), C.c_size_t(n), C.c_int(d), C.c_int(k), C.c_int(max_iter), C.c_uint64(seed), _vp(c), _vp(a),
+                                _vp(dist), C.byref(it), C.byref(mse)), "kmeans")
+    return c, a, dist, it.value, mse.value
+
+
+def pq_train(ctx: Context, x_raw, K: int, M: int, ksub: int = 256, perm=None, max_iter: int = 0, seed: int = 0):
+    """TrainPQ::IFVPQ (CoarseQuan + ProdQuan) on the device.  K == 0 trains the flat-ADC model (one zero centroid).
+    Returns (coarse [max(K,1),D], codebooks [M,ksub,D/M], mse [1+M])."""
+    x_raw = _f32(x_raw)
+    n, D = x_raw.shape
+    perm_a = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    coarse = np.empty((max(K, 1), D), dtype=np.float32)
+    cb = np.empty((M, ksub, D // max(M, 1)), dtype=np.float32)
+    mse = np.zeros(1 + M, dtype=np.float64)
+    _check(load().b200nn_pq_train(ctx.h, _vp(x_raw), C.c_size_t(n), C.c_int(D), C.c_int(K), C.c_int(M), C.c_int(ksub), _vp(perm_a),
+                                  C.c_int(max_iter), C.c_uint64(seed), _vp(coarse), _vp(cb), _vp(mse)), "pq_train")
+    return coarse, cb, mse
+
+
+def pq_write_model(path: str, coarse, codebooks, perm=None):
+    """TrainPQ::SaveCodebook's file (the one IVFOPQ::LoadModel reads)."""
+    coarse, codebooks = _f32(coarse), _f32(codebooks)
+    K, D = coarse.shape
+    M, ksub, _ = codebooks.shape
+    perm_a = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    _check(load().b200nn_pq_write_model(path.encode(), C.c_int(D), C.c_int(K), C.c_int(M), C.c_int(ksub), _vp(coarse), _vp(codebooks),
+                                        _vp(perm_a)), "pq_write_model")
+
+
+def kmeans_init_rows(n: int, k: int, seed: int):
+    """host-only: rows the initial centroids are copied from."""
+    r = np.empty(k, dtype=np.int32)
+    _check(load().b200nn_kmeans_init_rows(C.c_size_t(n), C.c_int(k), C.c_uint64(seed), _vp(r)), "kmeans_init_rows")
+    return r
+
+
+def kmeans_plan_update(assign, dist, k: int):
+    """host-only: one update's integer bookkeeping.  Returns (assign with donors moved, count, row_sorted, cluster_off)."""
+    a = np.ascontiguousarray(assign, dtype=np.int32).copy()
+    dist = _f32(dist)
+    n = a.shape[0]
+    count = np.empty(k, dtype=np.int32)
+    rows = np.empty(n, dtype=np.int32)
+    off = np.empty(k + 1, dtype=np.int64)
+    _check(load().b200nn_kmeans_plan_update(C.c_size_t(n), C.c_int(k), _vp(a), _vp(dist), _vp(count), _vp(rows), _vp(off)), "kmeans_plan_update")
+    return a, count, rows, off

@@ -10,7 +10,10 @@
 //     R = r0 + r1        (pre-split once per model on the host)
 //     y = x2*r0 + x1*r1 + x1*r0 + x0*r1 + x0*r0        (small terms first)
 // Every product of TF32-exact operands is exact in fp32; the only roundings are the fp32
-// accumulations in TMEM.  For a PERMUTATION matrix (r1 = 0, entries 0/1) every partial sum is
+// accumulations in TMEM, and those TRUNCATE (measured: a single accumulator over K = 1024 ends ~60 ulp
+// short, always toward zero).  So the leading product x0*r0 and the four correction products (2^-11 of the
+// result and less) accumulate in two separate TMEM column ranges and are added once in the epilogue:
+// one truncation per k-step on the leading sum instead of five.  For a PERMUTATION matrix (r1 = 0, entries 0/1) every partial sum is
 // exactly representable, so the result is bit-identical to the gather of IVFOPQ::reorder
 // (opq/src/IVFOPQ.cpp:424-439) -- tests/test_rotate_gemm_gpu.py checks that on the device.
 //
@@ -81,7 +84,7 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
     const int nchunks = K / RG_KC;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)NB) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * NB)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
@@ -143,11 +146,14 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
                 const uint64_t da0 = umma_desc_kmajor(A + ak, A_LBO, SBO), da1 = umma_desc_kmajor(A + A_PLANE + ak, A_LBO, SBO),
                                da2 = umma_desc_kmajor(A + 2 * A_PLANE + ak, A_LBO, SBO);
                 const uint64_t db0 = umma_desc_kmajor(B + bk, B_LBO, SBO), db1 = umma_desc_kmajor(B + B_PLANE + bk, B_LBO, SBO);
-                umma_tf32(tmem_base, da2, db0, idesc, (kc | s) != 0);  // first MMA of the tile overwrites the accumulator
-                umma_tf32(tmem_base, da1, db1, idesc, 1);
-                umma_tf32(tmem_base, da1, db0, idesc, 1);
-                umma_tf32(tmem_base, da0, db1, idesc, 1);
-                umma_tf32(tmem_base, da0, db0, idesc, 1);
+                // two accumulators (the tensor core TRUNCATES every fp32 accumulation): the four correction products,
+                // 2^-11 and less of the result, go to columns [NB, 2NB); the leading product x0*r0 to columns [0, NB).
+                // The first MMA into an accumulator overwrites it.  The epilogue adds the two (one rounding).
+                umma_tf32(tmem_base + NB, da2, db0, idesc, (kc | s) != 0);
+                umma_tf32(tmem_base + NB, da1, db1, idesc, 1);
+                umma_tf32(tmem_base + NB, da1, db0, idesc, 1);
+                umma_tf32(tmem_base + NB, da0, db1, idesc, 1);
+                umma_tf32(tmem_base, da0, db0, idesc, (kc | s) != 0);
             }
             umma_commit(stage_free + 8 * st);
             if (kc == nchunks - 1) umma_commit(accum_full);
@@ -170,17 +176,25 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     };
+    // y = leading accumulator + correction accumulator, one fp32 rounding
+    auto tld_sum = [&](float (&v)[32], int c0) {
+        uint32_t r[32], q[32];
+        tld32(r, c0);
+        tld32(q, NB + c0);
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = __fadd_rn(__uint_as_float(r[i]), __uint_as_float(q[i]));
+    };
     float denomv = 1.0f;
     if (MODE == 1) {  // thread = row: sum of squares over the row's N outputs, in column order, accumulated in double
         double ss = 0.0;
 #pragma unroll 1
         for (int c0 = 0; c0 < NB; c0 += 32) {
-            uint32_t r[32];
-            tld32(r, c0);
+            float v[32];
+            tld_sum(v, c0);
 #pragma unroll
             for (int i = 0; i < 32; i++) {
-                const double v = (double)__uint_as_float(r[i]);
-                ss = __dadd_rn(ss, __dmul_rn(v, v));
+                const double dv = (double)v[i];
+                ss = __dadd_rn(ss, __dmul_rn(dv, dv));
             }
         }
         const double d = (double)__fsqrt_rn((float)ss);
@@ -188,12 +202,12 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
     }
 #pragma unroll 1
     for (int c0 = 0; c0 < NB; c0 += 32) {
-        uint32_t r[32];
-        tld32(r, c0);
+        float v[32];
+        tld_sum(v, c0);
         if (valid) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-                float4 o = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 if (MODE == 1) { o.x = __fdiv_rn(o.x, denomv); o.y = __fdiv_rn(o.y, denomv); o.z = __fdiv_rn(o.z, denomv); o.w = __fdiv_rn(o.w, denomv); }
                 *reinterpret_cast<float4*>(yrow + c0 + i) = o;
             }
@@ -201,7 +215,7 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)NB) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * NB)) : "memory");
 }
 
 // ---- host ----

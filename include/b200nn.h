@@ -170,6 +170,36 @@ int b200nn_proj_apply_dev(b200nn_proj_t p, const float* x_dev, size_t n, int l2n
 int b200nn_rootsift(b200nn_ctx_t ctx, float* x, size_t n, int d, float eps);
 int b200nn_rootsift_dev(b200nn_ctx_t ctx, float* x_dev, size_t n, int d, float eps);
 
+/* ---- training ----------------------------------------------------------------
+ * TrainPQ (opq/train_codebook/train_PQ_codebook.h:23-54): CoarseQuan (train_PQ_codebook.cpp:150-199) = k-means with
+ * coarseK centroids over the reordered training rows + residue of every row; ProdQuan (:201-244) = one k-means with
+ * pq_k centroids per sub-space of the residue; SaveCodebook (:247-288) = the model file IVFOPQ::LoadModel reads.
+ * The reference calls yael's kmeans (un-vendored, random initialisation: numerically unpinned); here it is a
+ * deterministic Lloyd iteration (init, assignment arithmetic, update summation order, empty-cluster rule and stop rule
+ * are fixed: cvt_b200/csrc/capi_train.cu), all floating-point work on the device.
+ * max_iter = 0 means "until convergence" (capped at 10000 updates), as niter = 0 does in the reference. */
+int b200nn_kmeans(b200nn_ctx_t ctx, const float* x /*[n,d]*/, size_t n, int d, int k, int max_iter, uint64_t seed,
+                  float* centroids /*[k,d]*/, int32_t* assign /*[n] or NULL*/, float* dist /*[n] or NULL*/, int* iters_done /*or NULL*/,
+                  double* mse /*or NULL*/);
+/* host-only: the integer bookkeeping of that iteration, exported so that it can be checked without a device.
+ * init_rows: the k rows the initial centroids are copied from (splitmix64-driven partial Fisher-Yates).
+ * plan_update: one update's work on an assignment pass's result -- cluster sizes; every empty cluster (ascending) takes
+ * the farthest row (ties: lowest row) whose cluster keeps another row, `assign` is modified accordingly; stable counting
+ * sort: row_sorted[cluster_off[j] .. cluster_off[j+1]) = rows of cluster j, ascending. */
+int b200nn_kmeans_init_rows(size_t n, int k, uint64_t seed, int32_t* rows_out /*[k]*/);
+int b200nn_kmeans_plan_update(size_t n, int k, int32_t* assign /*[n] in/out*/, const float* dist /*[n]*/, int32_t* count /*[k]*/,
+                              int32_t* row_sorted /*[n]*/, int64_t* cluster_off /*[k+1]*/);
+/* x_raw [n,D] un-reordered rows (perm, if given, is applied first: TrainPQ::LoadFeatureSample :80,98,112).
+ * K >= 1: coarse [K,D] trained; K == 0: no coarse quantizer, coarse receives ONE all-zero centroid (the flat-ADC model).
+ * codebooks [M,ksub,D/M].  mse_out (NULL or 1+M doubles): mean squared quantisation error of the coarse stage and of
+ * each sub-space.  Sub-space m trains with seed + 1 + m. */
+int b200nn_pq_train(b200nn_ctx_t ctx, const float* x_raw, size_t n, int D, int K, int M, int ksub, const int32_t* perm /*or NULL*/,
+                    int max_iter, uint64_t seed, float* coarse, float* codebooks, double* mse_out);
+/* host-only: the OPQ model file, reorder tail written as int32[D] (identity when perm is NULL);
+ * the reference writer emits sizeof(int)*D bytes of a long-int array there (train_PQ_codebook.cpp:286). */
+int b200nn_pq_write_model(const char* path, int D, int K, int M, int ksub, const float* coarse, const float* codebooks,
+                          const int32_t* perm);
+
 #ifdef __cplusplus
 }
 #endif

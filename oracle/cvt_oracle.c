@@ -456,3 +456,143 @@ ORC_API void orc_rootsift(float* x, int64_t n, int d, float eps) {
         for (int j = 0; j < d; j++) v[j] = (float)((double)v[j] * scale);
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * training.  The reference trains with yael's kmeans
+ * (opq/train_codebook/train_PQ_codebook.cpp:164,229), an un-vendored dependency with random initialisation:
+ * PARITY UNPINNED at that boundary.  What is restated here is the product's own deterministic Lloyd iteration
+ * (cvt_b200/csrc/capi_train.cu states it), operation by operation, so that the device result can be checked bit
+ * for bit; the reference-shaped part is the arithmetic of the assignment (IVFOPQ.cpp:107-129, sqdist_seq above)
+ * and the structure CoarseQuan -> residue -> ProdQuan (train_PQ_codebook.cpp:150-244).
+ * ---------------------------------------------------------------------------------------- */
+#define ORC_KM_SUM_BLOCK 512
+
+static inline uint64_t orc_splitmix64(uint64_t* s) {
+    *s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = *s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+/* k-means over columns [col0, col0+d) of x[n][ld].  centroids [k][d]; assign [n], dist [n] (both required).
+ * On return assign/dist belong to the returned centroids.  Returns the number of updates performed, or -1 on bad input. */
+ORC_API int orc_kmeans(const float* x, int64_t n, int64_t ld, int col0, int d, int k, int max_iter, uint64_t seed,
+                       float* centroids, int32_t* assign, float* dist, double* mse) {
+    if (n < k || k < 1 || d < 1) return -1;
+    int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t* prev = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    int64_t* cnt = (int64_t*)malloc(sizeof(int64_t) * (size_t)k);
+    double* sum = (double*)malloc(sizeof(double) * (size_t)k * d);
+    double* part = (double*)malloc(sizeof(double) * (size_t)k * d);
+    int64_t* inblk = (int64_t*)malloc(sizeof(int64_t) * (size_t)k);
+    char* taken = (char*)malloc((size_t)n);
+    float* row = (float*)malloc(sizeof(float) * (size_t)d);
+    for (int64_t i = 0; i < n; i++) idx[i] = (int32_t)i;
+    uint64_t s = seed;
+    for (int j = 0; j < k; j++) { /* partial Fisher-Yates */
+        const int64_t r = j + (int64_t)(orc_splitmix64(&s) % (uint64_t)(n - j));
+        const int32_t t = idx[j]; idx[j] = idx[r]; idx[r] = t;
+        for (int t2 = 0; t2 < d; t2++) centroids[(int64_t)j * d + t2] = x[(int64_t)idx[j] * ld + col0 + t2];
+    }
+    const int cap = max_iter > 0 ? max_iter : 10000;
+    int iters = 0;
+    for (;;) {
+        for (int64_t i = 0; i < n; i++) { /* assignment: IVFOPQ.cpp:107-129 arithmetic */
+            for (int t = 0; t < d; t++) row[t] = x[i * ld + col0 + t];
+            int best = -1;
+            float dismin = (float)4294967295u;
+            for (int j = 0; j < k; j++) {
+                const float dd = sqdist_seq(row, centroids + (int64_t)j * d, d);
+                if (dd < dismin) { dismin = dd; best = j; }
+            }
+            assign[i] = best;
+            dist[i] = dismin;
+        }
+        int same = iters > 0, zero = 1;
+        for (int64_t i = 0; i < n; i++)
+            if (dist[i] != 0.0f) { zero = 0; break; }
+        if (same)
+            for (int64_t i = 0; i < n; i++)
+                if (assign[i] != prev[i]) { same = 0; break; }
+        if (same || zero || iters == cap) break;
+        for (int j = 0; j < k; j++) { cnt[j] = 0; inblk[j] = 0; }
+        for (int64_t i = 0; i < n; i++) {
+            if (assign[i] < 0) { iters = -1; goto done; }
+            cnt[assign[i]]++;
+        }
+        /* empty clusters, ascending: each takes the farthest row (ties: lowest row) among the rows not taken yet whose
+         * cluster keeps at least one other row; the row MOVES to the empty cluster before the means are formed */
+        memset(taken, 0, (size_t)n);
+        for (int j = 0; j < k; j++) {
+            if (cnt[j] != 0) continue;
+            int64_t far = -1;
+            for (int64_t i = 0; i < n; i++)
+                if (!taken[i] && cnt[assign[i]] >= 2 && (far < 0 || dist[i] > dist[far])) far = i;
+            taken[far] = 1;
+            cnt[assign[far]]--;
+            assign[far] = j;
+            cnt[j] = 1;
+        }
+        /* update: per cluster, rows in ascending order, blocks of 512 rows summed in double, block sums added in order */
+        for (int64_t e = 0; e < (int64_t)k * d; e++) { sum[e] = 0.0; part[e] = 0.0; }
+        for (int64_t i = 0; i < n; i++) {
+            const int a = assign[i];
+            for (int t = 0; t < d; t++) part[(int64_t)a * d + t] += (double)x[i * ld + col0 + t];
+            if (++inblk[a] == ORC_KM_SUM_BLOCK) {
+                for (int t = 0; t < d; t++) { sum[(int64_t)a * d + t] += part[(int64_t)a * d + t]; part[(int64_t)a * d + t] = 0.0; }
+                inblk[a] = 0;
+            }
+        }
+        for (int j = 0; j < k; j++)
+            for (int t = 0; t < d; t++) {
+                double sj = sum[(int64_t)j * d + t];
+                if (inblk[j]) sj += part[(int64_t)j * d + t];
+                centroids[(int64_t)j * d + t] = (float)(sj / (double)cnt[j]);
+            }
+        memcpy(prev, assign, sizeof(int32_t) * (size_t)n);
+        iters++;
+    }
+    if (mse) {
+        double tot = 0.0;
+        for (int64_t i = 0; i < n; i++) tot += (double)dist[i];
+        *mse = n ? tot / (double)n : 0.0;
+    }
+done:
+    free(idx); free(prev); free(cnt); free(sum); free(part); free(inblk); free(taken); free(row);
+    return iters;
+}
+
+/* TrainPQ::IFVPQ: LoadFeatureSample's reorder (:80,98,112), CoarseQuan (:150-199), ProdQuan (:201-244).
+ * K == 0: no coarse quantizer (one zero centroid).  mse_out: 1+M doubles or NULL. */
+ORC_API int orc_pq_train(const float* x_raw, int64_t n, int D, int K, int M, int ksub, const int32_t* perm, int max_iter,
+                         uint64_t seed, float* coarse, float* codebooks, double* mse_out) {
+    const int ds = D / M;
+    float* x = (float*)malloc(sizeof(float) * (size_t)n * D);
+    float* res = (float*)malloc(sizeof(float) * (size_t)n * D);
+    int32_t* assign = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    float* dist = (float*)malloc(sizeof(float) * (size_t)n);
+    int rc = 0;
+    double mse = 0.0;
+    for (int64_t r = 0; r < n; r++)
+        for (int i = 0; i < D; i++) x[r * D + i] = x_raw[r * D + (perm ? perm[i] : i)];
+    if (K >= 1) {
+        if (orc_kmeans(x, n, D, 0, D, K, max_iter, seed, coarse, assign, dist, &mse) < 0) { rc = -1; goto out; }
+        for (int64_t r = 0; r < n; r++)
+            for (int i = 0; i < D; i++) res[r * D + i] = x[r * D + i] - coarse[(int64_t)assign[r] * D + i];
+    } else {
+        for (int i = 0; i < D; i++) coarse[i] = 0.0f;
+        memcpy(res, x, sizeof(float) * (size_t)n * D);
+    }
+    if (mse_out) mse_out[0] = mse;
+    for (int m = 0; m < M; m++) {
+        if (orc_kmeans(res, n, D, m * ds, ds, ksub, max_iter, seed + 1 + (uint64_t)m, codebooks + (int64_t)m * ksub * ds, assign, dist, &mse) < 0) {
+            rc = -1;
+            goto out;
+        }
+        if (mse_out) mse_out[1 + m] = mse;
+    }
+out:
+    free(x); free(res); free(assign); free(dist);
+    return rc;
+}

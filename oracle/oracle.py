@@ -214,6 +214,38 @@ def rootsift(x, eps=1e-7):
     return y
 
 
+# ---------------------------------------------------------------------------- training (f-4)
+def kmeans(x, k, max_iter=0, seed=0):
+    """The product's deterministic Lloyd iteration restated (yael's kmeans is un-vendored: parity unpinned there).
+    Returns (centroids, assign, dist, iterations, mse)."""
+    x = _f32(x)
+    n, d = x.shape
+    c = np.empty((k, d), dtype=np.float32)
+    a = np.empty(n, dtype=np.int32)
+    dist = np.empty(n, dtype=np.float32)
+    mse = C.c_double(0.0)
+    it = lib().orc_kmeans(_p(x), C.c_int64(n), C.c_int64(d), C.c_int(0), C.c_int(d), C.c_int(k), C.c_int(max_iter), C.c_uint64(seed),
+                          _p(c), _p(a), _p(dist), C.byref(mse))
+    if it < 0:
+        raise ValueError("orc_kmeans: bad input")
+    return c, a, dist, it, mse.value
+
+
+def pq_train(x_raw, K, M, ksub=256, perm=None, max_iter=0, seed=0):
+    """TrainPQ::IFVPQ restated over the Lloyd iteration above.  Returns (coarse, codebooks, mse[1+M])."""
+    x_raw = _f32(x_raw)
+    n, D = x_raw.shape
+    perm_a = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+    coarse = np.empty((max(K, 1), D), dtype=np.float32)
+    cb = np.empty((M, ksub, D // M), dtype=np.float32)
+    mse = np.zeros(1 + M, dtype=np.float64)
+    rc = lib().orc_pq_train(_p(x_raw), C.c_int64(n), C.c_int(D), C.c_int(K), C.c_int(M), C.c_int(ksub),
+                            None if perm_a is None else _p(perm_a), C.c_int(max_iter), C.c_uint64(seed), _p(coarse), _p(cb), _p(mse))
+    if rc != 0:
+        raise ValueError("orc_pq_train: bad input")
+    return coarse, cb, mse
+
+
 # ---------------------------------------------------------------------------- compiled reference
 def parse_ref_opq(path: str) -> dict:
     b = open(path, "rb").read()

@@ -150,3 +150,12 @@ def frontend_sift_inputs(n: int = 80, d: int = 128):
     v[::7] *= np.float32(-1.0)
     v[3] = 0
     return v.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------- training (f-4)
+def train_inputs(n: int, d: int, seed: int = 0, centres: int = 40):
+    """Clustered rows (Gaussian blobs around seeded centres) for the k-means tests."""
+    rng = np.random.Generator(np.random.PCG64(0x7A11 + seed))
+    c = rng.standard_normal((centres, d), dtype=np.float32) * np.float32(2.0)
+    x = c[rng.integers(0, centres, n)] + rng.standard_normal((n, d), dtype=np.float32) * np.float32(0.5)
+    return np.ascontiguousarray(x, dtype=np.float32)

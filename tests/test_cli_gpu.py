@@ -31,6 +31,10 @@ def _records(td):
 
 def test_unmodified_reference_cli_on_gpu_index(tmp_path):
     exe = _need("ref_brute_force_on_b200nn")
+    # the binary must really bind the C ABI (a quoted #include resolves next to the reference source first: the build
+    # pipes the source through stdin for that reason and checks the same thing)
+    blob = open(exe, "rb").read()
+    assert b"b200nn_flat_search" in blob and b"b200nn_flat_add" in blob
     _records(str(tmp_path))
     r = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
