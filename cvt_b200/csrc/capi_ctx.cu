@@ -47,6 +47,7 @@ void b200nn_ctx_destroy(b200nn_ctx_t ctx) {
     for (int i = 0; i < 16; i++)
         if (ctx->c.events[i]) cudaEventDestroy(ctx->c.events[i]);
     if (ctx->c.d_err) cudaFree(ctx->c.d_err);
+    if (ctx->c.dmat) cudaFree(ctx->c.dmat);
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.own_stream);
     delete ctx;
 }

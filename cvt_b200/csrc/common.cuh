@@ -36,6 +36,8 @@ struct Ctx {
     uint64_t launches = 0;
     cudaEvent_t events[16] = {};
     int* d_err = nullptr;  // device-side error flag (smem layout overflow etc.)
+    float* dmat = nullptr;  // row-chunk distance matrix of the tiled nearest-centroid path (dist_tile.cu), grown on demand
+    size_t dmat_elems = 0;
 };
 
 // ------------------------------------------------------------------------------------ keys

@@ -14,6 +14,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "dist_tile.cuh"
 #include "pq_kernels.cuh"
 #include "topk.cuh"
 
@@ -942,6 +943,7 @@ int launch_rotate_perm(Ctx* ctx, const float* x, long long n, int D, const int* 
 
 int launch_coarse_assign(Ctx* ctx, const float* x, long long n, int D, const float* coarseT, int K, int* out_list) {
     if (n == 0) return 0;
+    if (tiled_nearest_pays(D, K)) return launch_tiled_nearest(ctx, x, D, 0, n, D, coarseT, K, 0, 1, out_list, nullptr);
     const int warps = 8;
     coarse_assign_kernel<<<grid_for(n, warps, ctx->sm_count), warps * 32, warps * D * sizeof(float), ctx->stream>>>(
         x, n, D, coarseT, K, out_list);
@@ -980,6 +982,7 @@ int launch_codes_to_scan_layout(Ctx* ctx, const unsigned char* codes, long long 
 int launch_coarse_probe(Ctx* ctx, const float* q, long long nq, int D, const float* coarseT, int K, int nk, int* out_lists) {
     if (nq == 0) return 0;
     if (nk > 8 || nk < 1 || nk > K) B2_FAIL(-1, "coarse_probe: nprobe must be in [1, min(8, K)]");
+    if (tiled_nearest_pays(D, K)) return launch_tiled_nearest(ctx, q, D, 0, nq, D, coarseT, K, 1, nk, out_lists, nullptr);
     const int warps = 4;
     coarse_probe_kernel<<<grid_for(nq, warps, ctx->sm_count), warps * 32, warps * D * sizeof(float), ctx->stream>>>(
         q, nq, D, coarseT, K, nk, out_lists);

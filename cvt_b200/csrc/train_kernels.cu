@@ -12,6 +12,7 @@
 // empty clusters) runs on the host; the O(n k d) and O(n d) floating-point work runs here.
 #include <algorithm>
 
+#include "dist_tile.cuh"
 #include "train_kernels.cuh"
 
 namespace b200nn {
@@ -137,6 +138,7 @@ int launch_kmeans_assign(Ctx* ctx, const float* x, long long ld, int col0, long 
                          float* dist) {
     if (n <= 0) return 0;
     if (d < 1 || d > 4096) B2_FAIL(-4, "kmeans: dimension must be in [1, 4096]");
+    if (tiled_nearest_pays(d, k)) return launch_tiled_nearest(ctx, x, ld, col0, n, d, cT, k, 0, 1, assign, dist);
     // rows per warp and warps per CTA from the shared-memory budget (<= 48 KB, no opt-in needed)
     const int R = (d <= 384) ? 4 : 1;
     int warps = 8;

@@ -36,6 +36,9 @@ def _bits(a):
     (480, 4, 20, 0, 5, True),        # 12 distinct points, k = 20: empty clusters, donors, stop on zero error
     (64, 6, 64, 0, 2, False),        # k = n
     (5000, 16, 1, 2, 8, False),      # k = 1: one cluster of 5000 rows = 10 summation blocks
+    (2000, 64, 96, 3, 11, False),    # d >= 32 and k >= 64: the register-tiled distance kernel (dist_tile.cu)
+    (1501, 40, 130, 2, 12, False),   # tiled, ragged: d = 16 + 16 + 8, two centroid tiles (ldm = 132), rows not a multiple of 128
+    (9000, 32, 4100, 1, 6, False),   # tiled, two row chunks of the distance matrix (128 MB / (4100 * 4 B) -> 8064 rows)
 ])
 def test_kmeans_bit_exact_vs_oracle(ctx, n, d, k, max_iter, seed, dup):
     from cvt_b200 import capi
