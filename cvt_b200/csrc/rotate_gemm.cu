@@ -107,8 +107,18 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
     const float* xrow = x + row * K;
     const uint32_t a_row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
 
+    // the row's next K chunk is fetched into registers while the current one is split and multiplied (the global-load
+    // latency would otherwise sit on the critical path of every chunk: 4 warps per SM cannot hide it by themselves)
+    float4 cur[RG_KC / 4], nxt[RG_KC / 4];
+    auto fetch = [&](float4 (&v)[RG_KC / 4], int kc) {
+#pragma unroll
+        for (int c = 0; c < RG_KC / 4; c++)
+            v[c] = valid ? __ldg(reinterpret_cast<const float4*>(xrow + kc * RG_KC + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    fetch(cur, 0);
     for (int kc = 0; kc < nchunks; kc++) {
         const int st = kc & 1, use = kc >> 1;
+        if (kc + 1 < nchunks) fetch(nxt, kc + 1);
         if (kc >= 2) mbar_wait(stage_free + 8 * st, (uint32_t)(use - 1) & 1u);  // MMAs of chunk kc-2 have drained this stage
         if (tid == 0) {
             mbar_arrive_expect_tx(b_full + 8 * st, 2 * B_PLANE);
@@ -118,8 +128,7 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
         const uint32_t a0 = sA + (uint32_t)st * 3 * A_PLANE + a_row_off;
 #pragma unroll
         for (int c = 0; c < RG_KC / 4; c++) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) v = __ldg(reinterpret_cast<const float4*>(xrow + kc * RG_KC + c * 4));
+            float4 v = cur[c];
             if (mean != nullptr) {  // cv::PCA::project subtracts the mean first (one fp32 rounding), then multiplies
                 const float4 mv = __ldg(reinterpret_cast<const float4*>(mean + kc * RG_KC + c * 4));
                 v.x = __fsub_rn(v.x, mv.x); v.y = __fsub_rn(v.y, mv.y); v.z = __fsub_rn(v.z, mv.z); v.w = __fsub_rn(v.w, mv.w);
@@ -134,6 +143,8 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
             sts128(o + A_PLANE, m0, m1, m2, m3);
             sts128(o + 2 * A_PLANE, l0, l1, l2, l3);
         }
+#pragma unroll
+        for (int c = 0; c < RG_KC / 4; c++) cur[c] = nxt[c];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {

@@ -31,6 +31,11 @@ for K, N, n in ((1024, 128, 1 << 17), (2048, 256, 1 << 16)):
     flop = 2.0 * n * K * N * 5
     print(f"proj {K}->{N} x {n} rows (+L2 norm): {ms:.3f} ms  {flop/ms/1e9:.1f} TF/s tf32 (5 products), "
           f"{(n*K*4 + n*N*4)/ms/1e6:.0f} GB/s of X+Y")
+    y0 = torch.empty((n, N), device="cuda")
+    p.reduce_dim_dev(x.data_ptr(), n, y0.data_ptr(), False)
+    ref = (x[:8192].double() - torch.from_numpy(mean).cuda().double()) @ torch.from_numpy(V).cuda().double().T
+    scale = torch.linalg.norm(x[:8192].double() - torch.from_numpy(mean).cuda().double(), dim=1, keepdim=True)
+    print("   un-normalised projection vs fp64: max |err| / |x - mean| = %.3e" % float(((y0[:8192].double() - ref).abs() / scale).max()))
     nrm = torch.linalg.norm(y, dim=1)
     print("   row norms in [%.7f, %.7f]" % (float(nrm.min()), float(nrm.max())))
     p.close()

@@ -45,4 +45,4 @@ q = synth.sift_like(4096, 128, seed=7)
 idx.search(q[:64], 10, nprobe=3)
 t0 = time.perf_counter()
 idx.search(q, 10, nprobe=3)
-print(f"IVF search 4096 queries, nprobe=3, K={K}, {idx.n_rows()} rows: {time.perf_counter() - t0:.4f} s")
+print(f"IVF search 4096 queries, nprobe=3, K={K}, {idx.n_rows} rows: {time.perf_counter() - t0:.4f} s")
