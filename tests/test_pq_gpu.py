@@ -288,3 +288,30 @@ def test_ivf_fused_search_vs_oracle(ctx, clamp):
         ntail += int((os_ == np.float32(clamp)).sum()) if np.isfinite(clamp) else int(np.isinf(os_).sum())
     assert ntail > 0 or not np.isfinite(clamp)  # the finite clamp case must exercise the id-ordered tail
     idx.close()
+
+
+def test_coarse_assign_and_probes_large_K_tiled(ctx):
+    """a2 + a4 on the register-tiled distance kernel (K >= 64): ragged K (not a multiple of the 128-centroid tile or of 4),
+    rows not a multiple of 128, DUPLICATED centroids (exact distance ties: the lowest index must win, IVFOPQ.cpp:123) and
+    probes in the reference's pop order."""
+    from cvt_b200 import capi
+    D, M, K, n, nq, nk = 64, 8, 1003, 3001, 77, 5
+    rng = np.random.Generator(np.random.PCG64(77))
+    x = synth.sift_like(n, D, seed=71)
+    q = synth.sift_like(nq, D, seed=72)
+    perm = synth.random_permutation(D, 73)
+    coarse = x[rng.choice(n, K, replace=False)][:, perm].copy()
+    coarse[500:520] = coarse[100:120]            # twenty exact duplicates at higher indices
+    cb = (rng.standard_normal((M, 256, D // M)) * 0.05).astype(np.float32)
+    idx = capi.PQIndex.create(ctx, coarse, cb, perm=perm)
+    xr = idx.rotate(x)
+    lists, codes = idx.encode(xr)
+    ol = orc.opq_coarse_assign(xr, coarse)
+    assert np.array_equal(lists, ol)
+    assert not np.isin(lists, np.arange(500, 520)).any() and np.isin(np.arange(100, 120), lists).any()
+    assert np.array_equal(codes, orc.opq_pq_encode(xr, coarse, ol, cb))
+    qr = idx.rotate(q)
+    probes, lut = idx.build_lut(qr, nprobe=nk)
+    for i in range(nq):
+        assert np.array_equal(probes[i], orc.opq_coarse_probe(qr[i], coarse, nk)), i
+    idx.close()
