@@ -107,17 +107,20 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
     const float* xrow = x + row * K;
     const uint32_t a_row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
 
-    // The row's K chunks are fetched into registers THREE chunks ahead of their use (four rotating buffers, the loop is
-    // unrolled by four so that the buffer index is a compile-time constant): with 4 warps per SM nothing else hides the
-    // HBM latency, and one chunk of look-ahead left the kernel latency-bound (1.9 us per chunk against 0.7 us of MMA).
-    float4 buf[4][RG_KC / 4];
+    // the row's next K chunk is fetched into registers while the current one is split and multiplied (the global-load
+    // latency would otherwise sit on the critical path of every chunk: 4 warps per SM cannot hide it by themselves).
+    // Measured: 0.499 -> 0.435 ms for 131 072 x 1024 -> 128.  Fetching THREE chunks ahead (four rotating buffers, 190
+    // registers) was tried and measured slower (0.481 ms; 0.894 vs 0.653 ms at 2048 -> 256): dropped.
+    float4 cur[RG_KC / 4], nxt[RG_KC / 4];
     auto fetch = [&](float4 (&v)[RG_KC / 4], int kc) {
 #pragma unroll
         for (int c = 0; c < RG_KC / 4; c++)
             v[c] = valid ? __ldg(reinterpret_cast<const float4*>(xrow + kc * RG_KC + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    auto chunk = [&](const float4 (&cur)[RG_KC / 4], int kc) {
+    fetch(cur, 0);
+    for (int kc = 0; kc < nchunks; kc++) {
         const int st = kc & 1, use = kc >> 1;
+        if (kc + 1 < nchunks) fetch(nxt, kc + 1);
         if (kc >= 2) mbar_wait(stage_free + 8 * st, (uint32_t)(use - 1) & 1u);  // MMAs of chunk kc-2 have drained this stage
         if (tid == 0) {
             mbar_arrive_expect_tx(b_full + 8 * st, 2 * B_PLANE);
@@ -142,6 +145,8 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
             sts128(o + A_PLANE, m0, m1, m2, m3);
             sts128(o + 2 * A_PLANE, l0, l1, l2, l3);
         }
+#pragma unroll
+        for (int c = 0; c < RG_KC / 4; c++) cur[c] = nxt[c];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
@@ -165,19 +170,6 @@ rotate_gemm_tf32x3_kernel(const float* __restrict__ x, long long n, int K, int N
             }
             umma_commit(stage_free + 8 * st);
             if (kc == nchunks - 1) umma_commit(accum_full);
-        }
-    };
-    fetch(buf[0], 0);
-    if (nchunks > 1) fetch(buf[1], 1);
-    if (nchunks > 2) fetch(buf[2], 2);
-    for (int kc0 = 0; kc0 < nchunks; kc0 += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int kc = kc0 + u;
-            if (kc < nchunks) {  // uniform across the CTA
-                if (kc + 3 < nchunks) fetch(buf[(u + 3) & 3], kc + 3);
-                chunk(buf[u], kc);
-            }
         }
     }
 
