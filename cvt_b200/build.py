@@ -89,7 +89,10 @@ def build_tools(force: bool = False, verbose: bool = False):
     compat = os.path.join(ROOT, "include", "b200nn", "compat")
     for ref_src, name, std, need in (
             ("/root/reference/brute_force_search/src/brute_force.cpp", "ref_brute_force_on_b200nn", "c++11", "b200nn_flat_search"),
-            ("/root/reference/opq/train_codebook/train_PQ.cpp", "ref_train_PQ_on_b200nn", "c++11", "b200nn_kmeans")):
+            ("/root/reference/opq/train_codebook/train_PQ.cpp", "ref_train_PQ_on_b200nn", "c++11", "b200nn_kmeans"),
+            # c++17: the test copy-initialises an Int8Quan from a temporary and the drop-in class is non-copyable
+            ("/root/reference/scalar_quantization/scalar_quantization/int8_quan_test.cpp", "ref_int8_quan_test_on_b200nn", "c++17",
+             "b200nn_sq_encode")):
         o = os.path.join(bdir, name)
         if os.path.exists(ref_src) and (force or _newer([ref_src, LIB] + hdrs, o)):
             with open(ref_src, "rb") as src:

@@ -159,3 +159,27 @@ def train_inputs(n: int, d: int, seed: int = 0, centres: int = 40):
     c = rng.standard_normal((centres, d), dtype=np.float32) * np.float32(2.0)
     x = c[rng.integers(0, centres, n)] + rng.standard_normal((n, d), dtype=np.float32) * np.float32(0.5)
     return np.ascontiguousarray(x, dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------- scalar quantizer fixture
+def int8_quan_test_vector():
+    """The 64-d input pinned by the reference's own test (scalar_quantization/scalar_quantization/int8_quan_test.cpp:26):
+    a ReLU-sparse embedding, 11 non-zero entries."""
+    v = np.zeros(64, dtype=np.float32)
+    for i, x in ((0, 0.7678224), (8, 2.6331244), (16, 0.583638), (17, 0.76271933), (25, 0.21529453), (28, 1.2015152), (40, 0.88310665),
+                 (43, 0.19277531), (50, 2.5779805), (53, 0.7728174), (55, 2.21898)):
+        v[i] = np.float32(x)
+    return v
+
+
+def write_ixsq_file(path: str, vmin, vdiff) -> None:
+    """faiss 1.5.3 IndexScalarQuantizer file as described in SURVEY.md App. A-8 (QT_8bit, RS_minmax, no stored codes)."""
+    import struct
+    d = len(vmin)
+    with open(path, "wb") as f:
+        f.write(b"IxSQ")
+        f.write(struct.pack("<iqqqBi", d, 0, 1 << 20, 1 << 20, 1, 1))           # index header
+        f.write(struct.pack("<iifQQ", 0, 0, 0.0, d, d))                          # qtype, rangestat, arg, d, code_size
+        f.write(struct.pack("<Q", 2 * d))
+        np.concatenate([np.asarray(vmin, np.float32), np.asarray(vdiff, np.float32)]).astype("<f4").tofile(f)
+        f.write(struct.pack("<Q", 0))
