@@ -680,17 +680,22 @@ int b200nn_pq_load_index(b200nn_ctx_t ctx, const char* path, const int32_t* perm
         B2_FAIL(B200NN_ERR_IO, "pq_load_index: truncated model section");
     }
     std::vector<int> lists, groups;
-    std::vector<unsigned char> codes;
+    std::vector<unsigned char> codes, blk;
+    const size_t rec = 4 + (size_t)M;  // int32 videoId + M code bytes per element (IVFOPQ.cpp:569-573)
     for (int k = 0; k < K; k++) {
         int32_t cnt = 0;
         if (fread(&cnt, 4, 1, f) != 1 || cnt < 0) { fclose(f); B2_FAIL(B200NN_ERR_IO, "pq_load_index: truncated list section"); }
-        for (int j = 0; j < cnt; j++) {
+        blk.resize((size_t)cnt * rec);
+        if (cnt && fread(blk.data(), rec, (size_t)cnt, f) != (size_t)cnt) { fclose(f); B2_FAIL(B200NN_ERR_IO, "pq_load_index: truncated element"); }
+        const size_t base = lists.size();
+        lists.resize(base + cnt, k);
+        groups.resize(base + cnt);
+        codes.resize((base + cnt) * (size_t)M);
+        for (size_t j = 0; j < (size_t)cnt; j++) {
             int32_t gid;
-            unsigned char cbuf[256];
-            if (fread(&gid, 4, 1, f) != 1 || fread(cbuf, 1, M, f) != (size_t)M) { fclose(f); B2_FAIL(B200NN_ERR_IO, "pq_load_index: truncated element"); }
-            lists.push_back(k);
-            groups.push_back(gid);
-            codes.insert(codes.end(), cbuf, cbuf + M);
+            memcpy(&gid, blk.data() + j * rec, 4);
+            groups[base + j] = gid;
+            memcpy(codes.data() + (base + j) * M, blk.data() + j * rec + 4, M);
         }
     }
     fclose(f);

@@ -161,3 +161,53 @@ def test_cfg4_shape_m32_d512(ctx):
         os_, oi = orc.topk_pairs(s, k)
         assert np.array_equal(Ig[qi].astype(np.int64), oi) and np.array_equal(Dg[qi].view(np.uint32), os_.view(np.uint32))
     idx.close()
+
+
+def test_cfg5_shard_shape_12p5m_rows_batch_16384(ctx, tmp_path, capsys):
+    """BASELINE configs[4] per GPU: one of 8 row shards of the 100M x 128 database = 12.5 M rows of M = 16 codes, the full
+    batch of 16384 queries, top-100.  The shard is loaded as an index file in the reference's own format (IVFOPQ::SaveIndex,
+    SURVEY.md App. A-3) holding seeded random codes, so that no 6.4 GB of raw vectors is needed; three queries are checked
+    bit for bit against a numpy restatement of the scan (sequential fp32 sum over m = 0..15 of LUT[m][code], then the k
+    smallest (score, row)); for all queries: ascending scores, ids in range, and the best id of a planted exact copy."""
+    from cvt_b200 import capi
+    n, D, M, B, k = 12_500_000, 128, 16, 16384, 100
+    rng = np.random.Generator(np.random.PCG64(0xCF65))
+    codes = rng.integers(0, 256, size=(n, M), dtype=np.uint8)
+    cb = (rng.standard_normal((M, 256, D // M)) * 0.09).astype(np.float32)
+    coarse = np.zeros((1, D), np.float32)
+    q = (rng.standard_normal((B, D)) * 0.09).astype(np.float32)
+    planted = 7_654_321                              # query 5 is exactly the reconstruction of this row: score 0, rank 0
+    q[5] = np.concatenate([cb[m][codes[planted, m]] for m in range(M)])
+    path = str(tmp_path / "shard.fvecs")
+    with open(path, "wb") as f:
+        np.array([D, 1, M, 256, 1], dtype="<i4").tofile(f)
+        coarse.tofile(f)
+        cb.tofile(f)
+        np.array([n], dtype="<i4").tofile(f)
+        rec = np.zeros(n, dtype=[("g", "<i4"), ("c", "u1", (M,))])
+        rec["c"] = codes
+        rec.tofile(f)
+        f.write(b"shard".ljust(260, b"\0"))
+    del rec
+    idx = capi.PQIndex.load_index(ctx, path, perm=None, clamp=float("inf"))
+    assert idx.n_rows == n
+    dist, ids = idx.search(q, k)                     # warm-up (builds the scan layout)
+    dist, ids = idx.search(q, k)
+    t = idx.last_timing()
+    with capsys.disabled():
+        alg = float(B) * n * M
+        print(f"\n[cfg5 shard] 12.5M rows x M=16, batch 16384, top-100: scan {t['scan_ms']:.1f} ms = {alg / t['scan_ms'] / 1e6:.0f} GB/s algorithmic, "
+              f"LUT {t['lut_ms']:.2f} ms, merge {t['merge_ms']:.2f} ms -> {B / (t['rotate_ms'] + t['lut_ms'] + t['scan_ms'] + t['merge_ms']) * 1e3:.0f} QPS per GPU")
+    assert np.all(np.diff(dist, axis=1) >= 0) and int(ids.max()) < n
+    assert ids[5, 0] == planted and dist[5, 0] == 0.0
+    for qi in (0, 5, B - 1):
+        lut = orc.opq_build_lut(q[qi], coarse[0], cb)            # [M, 256], a5 arithmetic
+        acc = np.zeros(n, dtype=np.float32)
+        for m in range(M):
+            acc = acc + lut[m][codes[:, m]]                       # a6: s = s + LUT[m][code[m]], m ascending, fp32
+        kth = np.partition(acc, k - 1)[k - 1]
+        cand = np.nonzero(acc <= kth)[0]
+        order = cand[np.lexsort((cand, acc[cand]))][:k]           # (score, row) ascending
+        assert np.array_equal(ids[qi].astype(np.int64), order), qi
+        assert np.array_equal(dist[qi].view(np.uint32), acc[order].view(np.uint32)), qi
+    idx.close()
