@@ -29,13 +29,15 @@
 #include "../b200nn.h"
 
 namespace b200nn {
-// one lazily created context per process (device from $B200NN_DEVICE, default 0)
+// one lazily created context per process (device from $B200NN_DEVICE, default 0); the function-local static is
+// initialised exactly once even when several host threads make their first call together (C++11)
 inline b200nn_ctx_t default_ctx() {
-    static b200nn_ctx_t ctx = nullptr;
-    if (!ctx) {
+    static b200nn_ctx_t ctx = []() {
+        b200nn_ctx_t c = nullptr;
         const char* e = std::getenv("B200NN_DEVICE");
-        if (b200nn_ctx_create(e ? std::atoi(e) : 0, &ctx) != 0) throw std::runtime_error(b200nn_last_error());
-    }
+        if (b200nn_ctx_create(e ? std::atoi(e) : 0, &c) != 0) throw std::runtime_error(b200nn_last_error());
+        return c;
+    }();
     return ctx;
 }
 inline void check(int rc) {
