@@ -131,3 +131,7 @@ def test_sharded_search_equals_single_index_world2():
 
 def test_sharded_search_equals_single_index_world4_grid():
     _run(4, [2, 4, 1])  # 2 row shards x 2 query chunks, and both pure layouts
+
+
+def test_sharded_search_equals_single_index_world8_grid():
+    _run(8, [2, 8])  # the grid planned for cfg3 on 8 GPUs (2 row shards x 4 query chunks) and plain row sharding
