@@ -139,6 +139,10 @@ def run_reference_sample(wl, inputs, n_queries, repeat, threads=0):
     if not orc.have_ref("ref_opq"):
         raise RuntimeError("oracle/_ref/ref_opq is missing (it is built in the container where /root/reference exists)")
     db, q, perm, coarse, cb = inputs
+    if threads <= 0:
+        # all host threads this process may use, stated explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers,
+        # which would otherwise silently turn the reference arm into a single-thread run
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     td = tempfile.mkdtemp(prefix="b200nn_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
         model, dbf, qf = write_reference_inputs(td, db, q, perm, coarse, cb)
