@@ -28,7 +28,7 @@ SYMBOLS = [
     "b200nn_pq_save_index", "b200nn_pq_load_index", "b200nn_pq_last_timing", "b200nn_pq_scan_bytes",
     "b200nn_sq_create", "b200nn_sq_destroy", "b200nn_sq_train_minmax", "b200nn_sq_encode", "b200nn_sq_decode",
     "b200nn_sq_encode_dev",
-    "b200nn_proj_create", "b200nn_proj_destroy", "b200nn_proj_apply", "b200nn_proj_apply_dev", "b200nn_rootsift", "b200nn_rootsift_dev",
+    "b200nn_proj_create", "b200nn_proj_load_model", "b200nn_pca_read_model", "b200nn_proj_destroy", "b200nn_proj_apply", "b200nn_proj_apply_dev", "b200nn_rootsift", "b200nn_rootsift_dev",
     "b200nn_kmeans", "b200nn_kmeans_init_rows", "b200nn_kmeans_plan_update", "b200nn_pq_train", "b200nn_pq_write_model",
 ]
 
@@ -409,6 +409,12 @@ class Projection:
         _check(load().b200nn_proj_create(ctx.h, C.c_int(self.K), C.c_int(self.N), _vp(mean_a), _vp(vectors), C.byref(self.h)), "proj_create")
         ctx._adopt(self)
 
+    @classmethod
+    def load_model(cls, ctx: Context, path: str):
+        """PCAUtils::loadModel: cv::PCA's YAML file (pca_train_project/model/*.yml)."""
+        mean, vectors, _ = pca_read_model(path)
+        return cls(ctx, vectors, mean)
+
     def close(self):
         if self.h:
             load().b200nn_proj_destroy(self.h)
@@ -494,3 +500,14 @@ def kmeans_plan_update(assign, dist, k: int):
     off = np.empty(k + 1, dtype=np.int64)
     _check(load().b200nn_kmeans_plan_update(C.c_size_t(n), C.c_int(k), _vp(a), _vp(dist), _vp(count), _vp(rows), _vp(off)), "kmeans_plan_update")
     return a, count, rows, off
+
+
+def pca_read_model(path: str):
+    """host-only: (mean [K], vectors [N,K], values [N]) of a cv::PCA YAML model (PCAUtils::loadModel, pca_utils.cc:16-23)."""
+    K, N = C.c_int(0), C.c_int(0)
+    _check(load().b200nn_pca_read_model(path.encode(), C.byref(K), C.byref(N), None, None, None), "pca_read_model")
+    mean = np.empty(K.value, dtype=np.float32)
+    vectors = np.empty((N.value, K.value), dtype=np.float32)
+    values = np.empty(N.value, dtype=np.float32)
+    _check(load().b200nn_pca_read_model(path.encode(), C.byref(K), C.byref(N), _vp(mean), _vp(vectors), _vp(values)), "pca_read_model")
+    return mean, vectors, values

@@ -162,6 +162,12 @@ int b200nn_sq_encode_dev(b200nn_sq_t sq, float* x_dev, size_t n, int l2norm, uin
  * K_in % 32 == 0, N_out % 64 == 0, and N_out in {64, 128, 256} when l2norm is requested. */
 int b200nn_proj_create(b200nn_ctx_t ctx, int K_in, int N_out, const float* mean /*[K_in] or NULL*/, const float* vectors,
                        b200nn_proj_t* out);
+/* PCAUtils::loadModel (pca_utils.cc:16-23): the model is cv::PCA's YAML as cv::FileStorage writes it (`vectors`, `values`,
+ * `mean` opencv-matrix nodes; shipped: pca_train_project/model/*.yml).  pca_read_model is host-only: with NULL buffers it
+ * returns the sizes, otherwise it fills mean [K_in], vectors [N_out, K_in] and/or values [N_out] (numbers parsed as double
+ * and narrowed to float, as OpenCV does).  proj_load_model = read + proj_create. */
+int b200nn_pca_read_model(const char* path, int* K_in, int* N_out, float* mean, float* vectors, float* values);
+int b200nn_proj_load_model(b200nn_ctx_t ctx, const char* path, b200nn_proj_t* out);
 void b200nn_proj_destroy(b200nn_proj_t p);
 int b200nn_proj_apply(b200nn_proj_t p, const float* x /*[n,K_in]*/, size_t n, int l2norm, float* y /*[n,N_out]*/);
 int b200nn_proj_apply_dev(b200nn_proj_t p, const float* x_dev, size_t n, int l2norm, float* y_dev);

@@ -59,6 +59,24 @@ def main():
     assert err < 2e-7, "restatement and cv2 disagree"
     np.savez_compressed(os.path.join(cases.GOLDEN, "frontend_pca.npz"), vectors=vectors, mean=mean, y=y, input_sha=cases.sha(x))
 
+    # a small cv::PCA model file written by cv::FileStorage itself (the format PCAUtils::loadModel reads), for the
+    # model-file reader of the C ABI; the arrays it holds are committed beside it
+    rng = np.random.Generator(np.random.PCG64(0x9CA))
+    q, _ = np.linalg.qr(rng.standard_normal((64, 64)))
+    small_vec = np.ascontiguousarray(q.astype(np.float32))
+    small_mean = (rng.standard_normal((1, 64)) * 0.3).astype(np.float32)
+    small_val = np.sort(rng.random((64, 1)).astype(np.float32), axis=0)[::-1].copy()
+    yml = os.path.join(cases.GOLDEN, "pca_small_64x64.yml")
+    fs_w = cv2.FileStorage(yml, cv2.FILE_STORAGE_WRITE)
+    fs_w.write("name", "PCA")
+    fs_w.write("vectors", small_vec)
+    fs_w.write("values", small_val)
+    fs_w.write("mean", small_mean)
+    fs_w.release()
+    fs_r = cv2.FileStorage(yml, cv2.FILE_STORAGE_READ)   # what OpenCV itself reads back (8 significant digits are printed)
+    np.savez_compressed(os.path.join(cases.GOLDEN, "pca_small_64x64.npz"), vectors=fs_r.getNode("vectors").mat(),
+                        values=fs_r.getNode("values").mat().reshape(-1), mean=fs_r.getNode("mean").mat().reshape(-1))
+
     d = cases.frontend_sift_inputs()
     r = root_sift_cv2(d)
     ro = orc.rootsift(d)

@@ -97,3 +97,36 @@ def test_scan_plan_tiles_the_work_exactly(lib, M):
                 assert slices == max(len(v) for v in cover.values())
             else:
                 assert slices == 1
+
+
+def test_pca_yaml_model_reader(lib, tmp_path):
+    """Host-only: PCAUtils::loadModel's file format (cv::PCA written by cv::FileStorage, pca_utils.cc:16-23).  The fixture
+    was written AND read back by cv2 in the build container (oracle/gen_golden_frontend.py); the reader must return the
+    same bits.  Where the reference tree is present, both shipped models are compared with cv2 as well."""
+    import numpy as np
+    from cvt_b200 import capi
+    G = os.path.join(ROOT, "tests", "golden")
+    gold = np.load(os.path.join(G, "pca_small_64x64.npz"))
+    mean, vectors, values = capi.pca_read_model(os.path.join(G, "pca_small_64x64.yml"))
+    assert vectors.shape == (64, 64) and mean.shape == (64,) and values.shape == (64,)
+    for got, want in ((mean, gold["mean"]), (vectors, gold["vectors"]), (values, gold["values"])):
+        assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want, dtype=np.float32).view(np.uint32))
+    with pytest.raises(capi.B200nnError):
+        capi.pca_read_model(str(tmp_path / "missing.yml"))
+    bad = tmp_path / "bad.yml"
+    bad.write_text("%YAML:1.0\n---\nname: PCA\nvectors: !!opencv-matrix\n   rows: 2\n   cols: 2\n   dt: f\n   data: [ 1., 2., 3. ]\n"
+                   "mean: !!opencv-matrix\n   rows: 1\n   cols: 2\n   dt: f\n   data: [ 0., 0. ]\n")
+    with pytest.raises(capi.B200nnError):
+        capi.pca_read_model(str(bad))  # 3 numbers for a 2 x 2 matrix
+    dbl = tmp_path / "dbl.yml"    # CV_64F nodes and no eigenvalues: accepted, narrowed to float, values = 0
+    dbl.write_text("%YAML:1.0\n---\nvectors: !!opencv-matrix\n   rows: 1\n   cols: 2\n   dt: d\n   data: [ 0.1, -2.5e-1 ]\n"
+                   "mean: !!opencv-matrix\n   rows: 1\n   cols: 2\n   dt: d\n   data: [ 1., 3. ]\n")
+    m2, v2, e2 = capi.pca_read_model(str(dbl))
+    assert np.array_equal(v2, np.array([[0.1, -0.25]], np.float32)) and np.array_equal(m2, [1.0, 3.0]) and not e2.any()
+    ref = "/root/reference/pca_train_project/model/pca_1024_128_300w_googlenet.yml"
+    if os.path.exists(ref):
+        cv2 = pytest.importorskip("cv2")
+        fs = cv2.FileStorage(ref, cv2.FILE_STORAGE_READ)
+        mean, vectors, values = capi.pca_read_model(ref)
+        assert np.array_equal(vectors.view(np.uint32), fs.getNode("vectors").mat().view(np.uint32))
+        assert np.array_equal(mean, fs.getNode("mean").mat().reshape(-1)) and np.array_equal(values, fs.getNode("values").mat().reshape(-1))

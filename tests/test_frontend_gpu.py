@@ -86,3 +86,16 @@ def test_projection_errors(ctx):
     with pytest.raises(capi.B200nnError):
         p.reduce_dim(np.zeros((3, 64), np.float32), l2norm=True)  # fused normalisation needs N in {64,128,256}
     p.close()
+
+
+def test_projection_from_yaml_model_file(ctx):
+    """PCAUtils::loadModel + reduceDim from a cv::PCA YAML file (fixture written by cv2, tests/golden/pca_small_64x64.yml)."""
+    from cvt_b200 import capi
+    gold = np.load(os.path.join(G, "pca_small_64x64.npz"))
+    proj = capi.Projection.load_model(ctx, os.path.join(G, "pca_small_64x64.yml"))
+    assert (proj.N, proj.K) == (64, 64)
+    x = cases.frontend_pca_inputs(64, 200)
+    y = proj.reduce_dim(x, l2norm=True)
+    o = orc.pca_project(x, gold["mean"], gold["vectors"], True)
+    assert float(np.abs(y - o).max()) <= 2e-5
+    proj.close()
