@@ -130,3 +130,26 @@ def test_pca_yaml_model_reader(lib, tmp_path):
         mean, vectors, values = capi.pca_read_model(ref)
         assert np.array_equal(vectors.view(np.uint32), fs.getNode("vectors").mat().view(np.uint32))
         assert np.array_equal(mean, fs.getNode("mean").mat().reshape(-1)) and np.array_equal(values, fs.getNode("values").mat().reshape(-1))
+
+
+@pytest.mark.parametrize("src,std,extra", [
+    ("brute_force_search/src/brute_force.cpp", "c++11", ["-fno-operator-names"]),
+    ("opq/src/multi_frame_index_test.cpp", "c++11", []),                      # the `#if 1` main (index build)
+    ("opq/src/multi_frame_index_test.cpp", "c++11", ["-DB200NN_FLIP_MAINS"]),  # the `#if 0` main (query), see below
+    ("opq/train_codebook/train_PQ.cpp", "c++11", []),
+    ("scalar_quantization/scalar_quantization/int8_quan_test.cpp", "c++17", []),
+])
+def test_reference_callers_compile_unmodified_against_the_dropin_headers(src, std, extra, tmp_path):
+    """INTEGRATION.md's claim, kept honest: the reference's own caller sources compile, unmodified, against
+    include/b200nn/compat (source piped through stdin so that quoted includes cannot pick up the reference's own headers
+    lying next to the file).  Only where the reference tree is present (the build container)."""
+    path = os.path.join("/root/reference", src)
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    text = open(path, "rb").read()
+    if "-DB200NN_FLIP_MAINS" in extra:  # select the file's second main the way its author does: by flipping the two #if lines
+        text = text.replace(b"#if 1", b"#if 0_", 1).replace(b"#if 0\n", b"#if 1\n", 1).replace(b"#if 0_", b"#if 0", 1)
+        extra = []
+    cmd = ["g++", "-std=" + std, "-fsyntax-only", "-I", os.path.join(ROOT, "include", "b200nn", "compat"), "-x", "c++", "-"] + extra
+    r = subprocess.run(cmd, input=text, capture_output=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr.decode(errors="replace")[:2000]
