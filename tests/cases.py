@@ -163,13 +163,8 @@ def train_inputs(n: int, d: int, seed: int = 0, centres: int = 40):
 
 # ------------------------------------------------------------------------------- scalar quantizer fixture
 def int8_quan_test_vector():
-    """The 64-d input pinned by the reference's own test (scalar_quantization/scalar_quantization/int8_quan_test.cpp:26):
-    a ReLU-sparse embedding, 11 non-zero entries."""
-    v = np.zeros(64, dtype=np.float32)
-    for i, x in ((0, 0.7678224), (8, 2.6331244), (16, 0.583638), (17, 0.76271933), (25, 0.21529453), (28, 1.2015152), (40, 0.88310665),
-                 (43, 0.19277531), (50, 2.5779805), (53, 0.7728174), (55, 2.21898)):
-        v[i] = np.float32(x)
-    return v
+    """The 64-d input pinned by the reference's own test (scalar_quantization/scalar_quantization/int8_quan_test.cpp:26)."""
+    return SQ_REF_TEST_VECTOR.copy()
 
 
 def write_ixsq_file(path: str, vmin, vdiff) -> None:

@@ -162,3 +162,61 @@ def test_frontend_restatement_equals_cv2_golden():
     r = orc.rootsift(d)
     assert np.array_equal(r.view(np.uint32), gr["y"].view(np.uint32))
     assert np.all(r[3] == 0)  # the all-zero descriptor stays zero (cv::normalize's epsilon guard)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Differential pinning beyond the committed goldens: fresh random inputs every seed, the restatement against the
+# UNMODIFIED reference compiled in place (oracle/_ref travels with the repo; skipped where it was never built).
+@pytest.mark.skipif(not orc.have_ref("ref_flat_bf_sse"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_flat_restatement_vs_reference_random(seed):
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    for d in (16, 100, 128):
+        n, nq, k = int(rng.integers(200, 700)), 7, int(rng.integers(1, 40))
+        coarse_grid = seed == 3  # few distinct values: masses of exact ties, the (dist, label) rule decides
+        x = (rng.integers(0, 4, (n, d)).astype(np.float32) * np.float32(0.25)) if coarse_grid else rng.standard_normal((n, d), dtype=np.float32)
+        q = (rng.integers(0, 4, (nq, d)).astype(np.float32) * np.float32(0.25)) if coarse_grid else rng.standard_normal((nq, d), dtype=np.float32)
+        labels = rng.permutation(n).astype(np.uint64) * np.uint64(3) + np.uint64(11)
+        xu = rng.integers(0, 4 if coarse_grid else 256, (n, d)).astype(np.uint8)
+        qu = rng.integers(0, 4 if coarse_grid else 256, (nq, d)).astype(np.uint8)
+        runs = [("bf_sse", "ip", 0, 4), ("hnsw", "ip", 0, 4), ("hnsw", "l2i", 2, 0)]
+        runs += [("bf_avx", "ip", 0, 8), ("hnsw", "l2", 1, 8)] if d % 16 == 0 else [("hnsw", "l2", 1, 4)]
+        for flav, metric, mcode, lanes in runs:
+            data, qq = (xu, qu) if metric == "l2i" else (x, q)
+            dist, lab = orc.run_ref_flat(flav, metric, data, labels, qq, k)
+            od, ol = orc.flat_search(mcode, lanes, data, labels, qq, k)
+            assert np.array_equal(lab, ol), (seed, d, flav, metric)
+            assert np.array_equal(dist.view(np.uint32), od.view(np.uint32)), (seed, d, flav, metric)
+
+
+@pytest.mark.skipif(not orc.have_ref("ref_opq"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,D,M,K,nk", [(1, 64, 8, 12, 3), (2, 128, 16, 1, 1), (3, 32, 4, 40, 2)])
+def test_opq_restatement_vs_reference_random(seed, D, M, K, nk, tmp_path):
+    """IVFOPQ::Add + QueryThrehold + get_sort_results on a fresh random model / database / queries."""
+    rng = np.random.Generator(np.random.PCG64(2000 + seed))
+    n, nq, rows_per_group, topk = 700, 9, 7, 5
+    db = synth.sift_like(n, D, seed=3000 + seed)
+    q = synth.sift_like(nq, D, seed=4000 + seed)
+    reorder = rng.permutation(D).astype(np.int32)
+    coarse = db[rng.choice(n, K, replace=False)][:, reorder].copy() if K > 1 else (rng.standard_normal((1, D)) * 0.02).astype(np.float32)
+    cb = (rng.standard_normal((M, 256, D // M)) * 0.08).astype(np.float32)
+    model = str(tmp_path / "m.model")
+    synth.write_opq_model(model, coarse, cb, reorder)
+    dbf = []
+    for gi, lo in enumerate(range(0, n, rows_per_group)):
+        p = str(tmp_path / f"db{gi}.bin")
+        synth.write_feat_file(p, db[lo:lo + rows_per_group])
+        dbf.append(p)
+    qp = str(tmp_path / "q.bin")
+    synth.write_feat_file(qp, q)
+    ref = orc.run_ref_opq(model, dbf, [qp], nk=nk, topk=topk, per_row=False)
+    x = orc.opq_reorder(db, reorder)
+    lists = orc.opq_coarse_assign(x, coarse)
+    assert np.array_equal(lists, ref["row_list"])
+    codes = orc.opq_pq_encode(x, coarse, lists, cb)
+    assert np.array_equal(codes, ref["codes"])
+    match = orc.opq_query_scores(orc.opq_reorder(q, reorder), coarse, cb, nk, lists, ref["row_group"], codes, ref["n_groups"], 1.0)
+    assert np.array_equal(_bits(match), _bits(ref["match"]))
+    for f in range(nq):
+        s, i = orc.topk_pairs(match[f], topk)
+        assert np.array_equal(i, ref["topk_id"][f]) and np.array_equal(_bits(s), _bits(ref["topk_score"][f]))
