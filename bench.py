@@ -49,6 +49,17 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
+def host_cpu_model():
+    """Model name of the host CPU the CPU baseline runs on (core count and model stated)."""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -263,7 +274,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["desc"], "n_rows": n, "dim": D, "M": M, "batch": B, "k": k, "nprobe": 1,
                            "step": f"{ns}-query sample of the batch per step"},
-                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": r["threads"], "kind": "reference",
+                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": r["threads"], "kind": "reference", "host": host_cpu_model(),
                                  "sample": f"{ns} of {B} queries per step x {args.steps + args.warmup} steps, unmodified IVFOPQ::QueryThrehold + "
                                            f"get_sort_results over {r['threads']} OpenMP threads; index built by IVFOPQ::Add in {r['build_s']:.1f}s"},
                 "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -448,7 +459,7 @@ def main():
             ids_equal = bool(np.array_equal(r["topk_id"], result_ids[:ns]))
             rel = np.abs(r["topk_score"] - result_d[:ns]) / np.maximum(np.abs(r["topk_score"]), 1e-30)
             recall10 = float(np.mean([len(set(r["topk_id"][i, :10]) & set(result_ids[i, :10])) / 10.0 for i in range(ns)]))
-            line["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": r["threads"], "kind": "reference",
+            line["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": r["threads"], "kind": "reference", "host": host_cpu_model(),
                                     "sample": f"first {ns} of {B} queries, unmodified IVFOPQ::QueryThrehold + get_sort_results over "
                                               f"{r['threads']} OpenMP threads (index built by IVFOPQ::Add, {r['build_s']:.1f}s, untimed)"}
             line["parity"] = {"vs": "unmodified reference (oracle/_ref/ref_opq)", "queries_checked": ns, "topk_ids_identical": ids_equal,
