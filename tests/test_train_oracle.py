@@ -136,3 +136,36 @@ def test_host_bookkeeping_argument_checks():
         capi.kmeans_plan_update(np.array([0, -1, 1], np.int32), np.zeros(3, np.float32), 2)  # a row without a centroid
     r = capi.kmeans_init_rows(1000, 1000, 7)
     assert sorted(r.tolist()) == list(range(1000))  # k = n: a permutation
+
+
+def test_plan_update_random_cases_against_a_python_restatement():
+    """The empty-cluster rule and the stable counting sort of b200nn_kmeans_plan_update on 200 random small assignments
+    (many empty clusters, distance ties, clusters of one row), against a direct Python statement of the rule."""
+    from cvt_b200 import capi
+    rng = np.random.Generator(np.random.PCG64(0xE5))
+    for case in range(200):
+        k = int(rng.integers(1, 12))
+        n = int(rng.integers(k, 40))
+        used = rng.choice(k, size=int(rng.integers(1, k + 1)), replace=False)       # clusters that own rows
+        assign = used[rng.integers(0, len(used), n)].astype(np.int32)
+        dist = (rng.integers(0, 4, n) * 0.5).astype(np.float32)                      # ties are the norm
+        a2, count, rows, off = capi.kmeans_plan_update(assign, dist, k)
+        # ---- the rule, stated directly
+        ea = assign.copy()
+        cnt = np.bincount(ea, minlength=k)
+        taken = np.zeros(n, bool)
+        for j in range(k):
+            if cnt[j]:
+                continue
+            best = -1
+            for i in range(n):
+                if not taken[i] and cnt[ea[i]] >= 2 and (best < 0 or dist[i] > dist[best]):
+                    best = i
+            taken[best] = True
+            cnt[ea[best]] -= 1
+            ea[best] = j
+            cnt[j] = 1
+        assert np.array_equal(a2, ea), case
+        assert np.array_equal(count, cnt) and count.min() >= 1
+        assert off[0] == 0 and off[-1] == n and np.array_equal(np.diff(off), cnt)
+        assert np.array_equal(rows, np.argsort(ea, kind="stable")), case
