@@ -1097,21 +1097,14 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
                        int n_full, int n_tail, const int4* tail_desc, int k, float clamp, uint32_t id_base,
                        unsigned long long* out_keys, float* warm_scratch) {
     using C = ScanCfg<G, WARPS_>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
+    // the opt-in is per device (a process may hold contexts on several GPUs): set it on every launch, it is a cheap host call
+    B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const long long n_gran = (n_rows + 63) / 64;
     const unsigned grid = (unsigned)(n_full + n_tail);
     int soft = C::SOFT;
     if (const char* e = getenv("B200NN_SOFT")) soft = std::max(1, std::min(C::SB - 4, atoi(e)));
     if (getenv("B200NN_SCAN_STATS")) {  // development aid: counters of the candidate path, printed per launch
-        static bool attr_set_s = false;
-        if (!attr_set_s) {
-            B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-            attr_set_s = true;
-        }
+        B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         unsigned long long* d_stats = nullptr;
         unsigned long long hs[16];
         B2_CUDA(cudaMalloc(&d_stats, sizeof(hs)));

@@ -17,10 +17,14 @@
  *     fixtures and on synthetic data, and against tests/golden/.
  *   - flat_* functions: pinned against the reference's hnswlib headers compiled in place
  *     (oracle/_ref/ref_flat) on synthetic data, and against tests/golden/.
- *   - sq_* functions: PARITY UNPINNED at the faiss boundary.  faiss 1.5.3 is an un-vendored
- *     dependency and the reference ships no trained model for its SQ tests; these functions
- *     restate the reference's own in-tree arithmetic (int8_quan.cc) and faiss 1.5.3's published
- *     QT_8bit non-uniform codec.
+ *   - sq_l2normalize / sq_encode / sq_decode: pinned against the UNMODIFIED reference class
+ *     (oracle/_ref/ref_int8_quan = scalar_quantization/scalar_quantization/int8_quan.cc compiled in
+ *     place against stand-ins for its two un-vendored dependencies, oracle/stubs/): the arithmetic of
+ *     L2NormalizeVector, Int8Encode and Int8Decode(std::string&) is the reference's own and reads
+ *     only sq.trained / sq.code_size from faiss.  Goldens tests/golden/sq_d*.npz are reference-run.
+ *   - sq_decode_faiss, sq_train_minmax: PARITY UNPINNED -- they restate faiss 1.5.3 itself
+ *     (ScalarQuantizer::decode, RS_minmax training), an un-vendored dependency; no faiss build and
+ *     no trained model exist here, so the published algorithm is all there is to follow.
  */
 #include <math.h>
 #include <stdint.h>
@@ -346,7 +350,7 @@ ORC_API void orc_flat_search(int metric, int L, const void* data, const uint64_t
 }
 
 /* ------------------------------------------------------------------------------------------
- * scalar_quantization/  (Int8Quan)  -- PARITY UNPINNED at the faiss 1.5.3 boundary.
+ * scalar_quantization/  (Int8Quan)  -- reference-run except the two faiss-internal routines (see the header).
  * ---------------------------------------------------------------------------------------- */
 
 /* Int8Quan::L2NormalizeVector, scalar_quantization/scalar_quantization/int8_quan.cc:46-56:

@@ -327,3 +327,62 @@ def run_ref_flat(flavour: str, metric: str, data, labels, queries, k: int, save_
     dist = raw[:, :, :4].copy().view("<i4" if u8 else "<f4").reshape(nq, k)
     lab = raw[:, :, 4:].copy().view("<u8").reshape(nq, k)
     return dist, lab
+
+
+def run_ref_int8_quan(x, vmin, vdiff, l2norm=True, via_conf: bool = False, source: int = 0) -> dict:
+    """Run the UNMODIFIED cvtk::quant::Int8Quan (scalar_quantization/scalar_quantization/int8_quan.cc compiled in place
+    against the stub faiss / nlohmann headers, oracle/Makefile) on rows x with the trained range [vmin | vdiff] written as
+    an IxSQ model file.  via_conf drives the multi-model constructor (a JSON conf naming `source`+1 models; the queried
+    one is the last).  Returns the reference's own outputs: codes / x_after (Int8Encode, :72-94), normed
+    (L2NormalizeVector, :46-56), decode (Int8Decode(std::string&), :117-132) -- reference-run -- and codes_faiss /
+    decode_faiss, which pass through the STUB codec (faiss itself is absent) and stay unpinned."""
+    import struct
+    exe = os.path.join(REF_DIR, "ref_int8_quan")
+    x = _f32(x)
+    n, d = x.shape
+    vmin, vdiff = _f32(vmin), _f32(vdiff)
+
+    def write_model(path, vm, vd):
+        with open(path, "wb") as f:  # faiss 1.5.x IndexScalarQuantizer layout, SURVEY.md App. A-8
+            f.write(b"IxSQ")
+            f.write(struct.pack("<iqqqBi", d, 0, 1 << 20, 1 << 20, 1, 1))
+            f.write(struct.pack("<iifQQ", 0, 0, 0.0, d, d))
+            f.write(struct.pack("<Q", 2 * d))
+            np.concatenate([vm, vd]).astype("<f4").tofile(f)
+            f.write(struct.pack("<Q", 0))
+
+    with tempfile.TemporaryDirectory() as td:
+        model = os.path.join(td, "m.bin")
+        write_model(model, vmin, vdiff)
+        arg_model, num_source = model, 0
+        if via_conf:
+            conf = {}
+            for i in range(source):  # decoys in front of the model under test
+                dp = os.path.join(td, f"decoy{i}.bin")
+                write_model(dp, vmin + np.float32(1.0 + i), vdiff * np.float32(2.0))
+                conf[str(i)] = {"model_path": dp}
+            conf[str(source)] = {"model_path": model}
+            arg_model = os.path.join(td, "conf.json")
+            json.dump(conf, open(arg_model, "w"))
+            num_source = source + 1
+        rows, out = os.path.join(td, "rows.f32"), os.path.join(td, "out.bin")
+        x.tofile(rows)
+        r = subprocess.run([exe, arg_model, str(num_source), str(source if via_conf else 0), rows, str(n), str(d), "1" if l2norm else "0", out],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"ref_int8_quan failed: {r.stderr}")
+        b = open(out, "rb").read()
+    status, n2, d2 = np.frombuffer(b, "<i4", 3)
+    assert status == 1 and n2 == n and d2 == d, f"ref_int8_quan status {status}"
+    off = 12
+    nd = n * d
+
+    def take(dtype, size):
+        nonlocal off
+        a = np.frombuffer(b, dtype, nd, off).reshape(n, d).copy()
+        off += nd * size
+        return a
+    res = dict(codes=take("u1", 1), x_after=take("<f4", 4), normed=take("<f4", 4), decode=take("<f4", 4), codes_faiss=take("u1", 1),
+               decode_faiss=take("<f4", 4))
+    res["rc_bad_dims"] = int(np.frombuffer(b, "<i4", 1, off)[0])
+    return res

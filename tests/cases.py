@@ -167,6 +167,15 @@ def int8_quan_test_vector():
     return SQ_REF_TEST_VECTOR.copy()
 
 
+def int8_quan_test_model():
+    """The seeded trained range the int8_quan_test mains (reference and drop-in) load as their model."""
+    rng = np.random.Generator(np.random.PCG64(64))
+    vmin = (-rng.random(64) * 0.02).astype(np.float32)
+    vdiff = (rng.random(64) * 0.6 + 0.05).astype(np.float32)
+    vdiff[5] = 0.0                                        # a constant dimension: code 0 (int8_quan.cc:82)
+    return vmin, vdiff
+
+
 def write_ixsq_file(path: str, vmin, vdiff) -> None:
     """faiss 1.5.3 IndexScalarQuantizer file as described in SURVEY.md App. A-8 (QT_8bit, RS_minmax, no stored codes)."""
     import struct

@@ -131,12 +131,14 @@ def test_flat_save_load_byte_format(ctx, tmp_path):
 
 
 @pytest.mark.parametrize("d", [64, 128])
-def test_sq_vs_restatement(ctx, d):
-    """PARITY UNPINNED at the faiss boundary (see oracle header): compared with the restatement of
-    int8_quan.cc and with its committed golden output."""
+def test_sq_vs_reference_golden(ctx, d):
+    """codes / x_normed / decode of the golden are REFERENCE-RUN (the unmodified int8_quan.cc compiled against stand-ins for
+    its un-vendored dependencies, oracle/gen_golden.py::gen_sq): Int8Encode, L2NormalizeVector and Int8Decode(std::string&)
+    on the GPU must equal them bit for bit.  decode_faiss (faiss's own all-float decode) is the one unpinned output."""
     from cvt_b200 import capi
     c = cases.sq_case(d)
     gold = np.load(os.path.join(G, f"sq_d{d}.npz"))
+    assert bool(gold["pinned"]) and str(gold["input_sha"]) == c["input_sha"]
     sq = capi.SQ(ctx, c["vmin"], c["vdiff"])
     codes, xn = sq.encode(c["x"], l2norm=True)
     assert np.array_equal(codes, gold["codes"])

@@ -113,9 +113,11 @@ def test_flat_tie_rule_is_lexicographic():
 
 
 @pytest.mark.parametrize("d", [64, 128])
-def test_sq_restatement_self_consistency(d):
-    # parity UNPINNED at the faiss boundary (no model shipped, faiss un-vendored): the golden is the
-    # restatement's own output; this guards against drift and checks the documented properties.
+def test_sq_restatement_vs_reference_golden(d):
+    # codes / x_normed / decode in the golden are REFERENCE-RUN: produced by the unmodified int8_quan.cc compiled against
+    # stand-ins for faiss / nlohmann (oracle/Makefile, oracle/gen_golden.py::gen_sq).  decode_faiss (faiss's own
+    # all-float decode) stays unpinned: faiss is absent, the golden there is the restatement's own output.
+    assert bool(np.load(os.path.join(G, f"sq_d{d}.npz"))["pinned"])
     c = cases.sq_case(d)
     gold = np.load(os.path.join(G, f"sq_d{d}.npz"))
     assert str(gold["input_sha"]) == c["input_sha"]
@@ -220,3 +222,36 @@ def test_opq_restatement_vs_reference_random(seed, D, M, K, nk, tmp_path):
     for f in range(nq):
         s, i = orc.topk_pairs(match[f], topk)
         assert np.array_equal(i, ref["topk_id"][f]) and np.array_equal(_bits(s), _bits(ref["topk_score"][f]))
+
+
+@pytest.mark.skipif(not orc.have_ref("ref_int8_quan"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_sq_restatement_vs_reference_random(seed):
+    """Int8Quan::L2NormalizeVector / Int8Encode / Int8Decode(std::string&) of the unmodified int8_quan.cc (compiled against
+    the faiss / nlohmann stand-ins) on fresh random rows and trained ranges: the restatement must equal it bit for bit.
+    Seeds 3, 4 go through the multi-model constructor (JSON conf, source 1 / 2)."""
+    rng = np.random.Generator(np.random.PCG64(7000 + seed))
+    d = int(rng.choice([32, 64, 100, 128, 256]))
+    n = int(rng.integers(40, 160))
+    x = (rng.standard_normal((n, d), dtype=np.float32) * np.float32(rng.uniform(0.2, 3.0))).astype(np.float32)
+    if seed % 2 == 0:
+        x = np.maximum(x, 0)                       # ReLU-sparse rows, as the reference's own test vector
+    x[0] = 0                                       # max(1e-12, norm) guard
+    x[1] *= np.float32(1e-20)                      # denormal-range squares: accum is double, the quotient stays finite
+    x[2] *= np.float32(1e6)
+    xn = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)
+    sub = xn[rng.choice(n, n // 2, replace=False)]  # range trained on a subset: some values fall outside (clamp to 0 / 255)
+    vmin = sub.min(0).astype(np.float32)
+    vdiff = (sub.max(0) - vmin).astype(np.float32)
+    vdiff[int(rng.integers(d))] = 0                # constant dimension
+    for l2norm in (True, False):
+        ref = orc.run_ref_int8_quan(x, vmin, vdiff, l2norm=l2norm, via_conf=seed >= 3, source=seed - 2 if seed >= 3 else 0)
+        codes, xa = orc.sq_encode(x, vmin, vdiff, l2norm=l2norm)
+        assert np.array_equal(codes, ref["codes"]), (seed, l2norm)
+        assert np.array_equal(_bits(xa), _bits(ref["x_after"])), (seed, l2norm)
+        nrm = x.copy()
+        for i in range(n):
+            orc.lib().orc_sq_l2normalize(orc._p(nrm[i]), d)
+        assert np.array_equal(_bits(nrm), _bits(ref["normed"]))
+        assert np.array_equal(_bits(orc.sq_decode(codes, vmin, vdiff)), _bits(ref["decode"])), (seed, l2norm)
+        assert ref["rc_bad_dims"] == 0             # n_dims % code_size != 0 -> 0 (int8_quan.cc:73-75)
