@@ -61,7 +61,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(lambda j: _run(*j), jobs))
     if force or jobs or not os.path.exists(LIB):
-        _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs, os.path.join(OBJDIR, "link.log"))
+        _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl", "-lpthread"], os.path.join(OBJDIR, "link.log"))
     return LIB
 
 

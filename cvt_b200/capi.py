@@ -20,12 +20,17 @@ SYMBOLS = [
     "b200nn_last_error", "b200nn_version", "b200nn_ctx_create", "b200nn_ctx_destroy", "b200nn_ctx_set_stream",
     "b200nn_ctx_synchronize", "b200nn_ctx_launch_count", "b200nn_ctx_event_record", "b200nn_ctx_event_elapsed_ms",
     "b200nn_flat_create", "b200nn_flat_destroy", "b200nn_flat_add", "b200nn_flat_remove", "b200nn_flat_size",
-    "b200nn_flat_search", "b200nn_flat_search_dev", "b200nn_flat_save", "b200nn_flat_load",
+    "b200nn_flat_search", "b200nn_flat_search_dev", "b200nn_flat_save", "b200nn_flat_load", "b200nn_flat_load_hnsw", "b200nn_flat_info",
     "b200nn_pq_create", "b200nn_pq_load_model", "b200nn_pq_destroy", "b200nn_pq_set_clamp", "b200nn_pq_info",
     "b200nn_pq_rotate", "b200nn_pq_encode", "b200nn_pq_add", "b200nn_pq_add_dev", "b200nn_pq_add_rotated", "b200nn_pq_get_rows",
     "b200nn_pq_build_lut", "b200nn_pq_scores", "b200nn_pq_query_groups", "b200nn_pq_search", "b200nn_pq_search_dev", "b200nn_topk_merge_dev",
     "b200nn_topk_merge_grid_dev", "b200nn_pq_scan_plan",
-    "b200nn_pq_save_index", "b200nn_pq_load_index", "b200nn_pq_last_timing", "b200nn_pq_scan_bytes",
+    "b200nn_pq_save_index", "b200nn_pq_save_index_n", "b200nn_pq_load_index", "b200nn_pq_last_timing", "b200nn_pq_scan_bytes",
+    "b200nn_pq_scores_dev", "b200nn_pq_append_coded",
+    "b200nn_comm_get_unique_id", "b200nn_comm_create", "b200nn_comm_destroy", "b200nn_comm_info", "b200nn_pq_search_sharded_dev",
+    "b200nn_plan_layout", "b200nn_mpq_create", "b200nn_mpq_load_model", "b200nn_mpq_destroy", "b200nn_mpq_info", "b200nn_mpq_shard_rows", "b200nn_mpq_set_clamp",
+    "b200nn_mpq_rotate", "b200nn_mpq_add", "b200nn_mpq_add_rotated", "b200nn_mpq_search", "b200nn_mpq_scores", "b200nn_mpq_save_index",
+    "b200nn_mpq_load_index",
     "b200nn_sq_create", "b200nn_sq_destroy", "b200nn_sq_train_minmax", "b200nn_sq_encode", "b200nn_sq_decode",
     "b200nn_sq_encode_dev",
     "b200nn_proj_create", "b200nn_proj_load_model", "b200nn_pca_read_model", "b200nn_proj_destroy", "b200nn_proj_apply", "b200nn_proj_apply_dev", "b200nn_rootsift", "b200nn_rootsift_dev",
@@ -276,6 +281,20 @@ class PQIndex:
                                            C.c_void_p(out_dist_ptr), C.c_void_p(out_id_ptr), C.c_void_p(out_key_ptr),
                                            C.c_uint64(id_base)), "pq_search_dev")
 
+    def search_sharded_dev(self, comm: "Comm", row_shards: int, q_dev_ptr: int, nq: int, k: int, nprobe: int, id_base: int,
+                           out_dist_ptr: int, out_id_ptr: int):
+        """One step of the sharded search on this rank (collective over comm): local scan of this rank's query chunk ->
+        one ncclAllGather of the per-rank records -> merge.  q_dev_ptr = the whole batch."""
+        _check(load().b200nn_pq_search_sharded_dev(self.h, comm.h, C.c_int(row_shards), C.c_void_p(q_dev_ptr), C.c_size_t(nq), C.c_int(nprobe),
+                                                   C.c_size_t(k), C.c_uint64(id_base), C.c_void_p(out_dist_ptr), C.c_void_p(out_id_ptr)),
+               "pq_search_sharded_dev")
+
+    def append_coded(self, lists, codes, group_ids=None):
+        lists = np.ascontiguousarray(lists, dtype=np.int32)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        g = None if group_ids is None else np.ascontiguousarray(group_ids, dtype=np.int32)
+        _check(load().b200nn_pq_append_coded(self.h, _vp(lists), _vp(g), _vp(codes), C.c_size_t(lists.shape[0])), "pq_append_coded")
+
     def last_timing(self):
         ms = (C.c_float * 4)()
         _check(load().b200nn_pq_last_timing(self.h, ms), "pq_last_timing")
@@ -286,6 +305,156 @@ class PQIndex:
         if group_paths is not None:
             arr = (C.c_char_p * len(group_paths))(*[p.encode() for p in group_paths])
         _check(load().b200nn_pq_save_index(self.h, dir_or_path.encode(), arr), "pq_save_index")
+
+
+COMM_ID_BYTES = 128
+
+
+def plan_layout(n_ranks: int, n_rows: int, batch: int, M: int, k: int, sm_count: int = 148):
+    """(row shards R, query chunks Q) of the rank grid, from the library's cost model (host-only)."""
+    r, q = C.c_int(), C.c_int()
+    _check(load().b200nn_plan_layout(C.c_int(n_ranks), C.c_uint64(n_rows), C.c_uint64(batch), C.c_int(M), C.c_int(k), C.c_int(sm_count),
+                                     C.byref(r), C.byref(q)), "plan_layout")
+    return r.value, q.value
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 draws it, every rank passes it to Comm)."""
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    _check(load().b200nn_comm_get_unique_id(buf), "comm_get_unique_id")
+    return bytes(buf)
+
+
+class Comm:
+    """One rank of a multi-GPU job: NCCL communicator (ncclCommInitRank) + exchange buffers, owned by the C library."""
+
+    def __init__(self, ctx: Context, rank: int, nranks: int, unique_id: bytes | None):
+        self.h = C.c_void_p()
+        idb = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(unique_id) if unique_id is not None else None
+        _check(load().b200nn_comm_create(ctx.h, C.c_int(rank), C.c_int(nranks), idb, C.byref(self.h)), "comm_create")
+        self.ctx, self.rank, self.nranks = ctx, rank, nranks
+        ctx._adopt(self)
+
+    def nccl_version(self) -> int:
+        v = C.c_int()
+        _check(load().b200nn_comm_info(self.h, None, None, C.byref(v)), "comm_info")
+        return int(v.value)
+
+    def close(self):
+        if self.h:
+            load().b200nn_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiPQ:
+    """IVFOPQ drop-in row-sharded over several GPUs of THIS process (b200nn_mpq_*): host buffers in and out."""
+
+    def __init__(self, handle):
+        self.h = handle
+        D, K, M, ks, nd, pe = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(load().b200nn_mpq_info(self.h, C.byref(D), C.byref(K), C.byref(M), C.byref(ks), None, None, C.byref(nd), C.byref(pe)), "mpq_info")
+        self.D, self.K, self.M, self.ksub, self.n_devices, self.peer_exchange = D.value, K.value, M.value, ks.value, nd.value, bool(pe.value)
+
+    @staticmethod
+    def _devs(devices):
+        d = np.ascontiguousarray(devices, dtype=np.int32)
+        return d, C.c_int(d.shape[0])
+
+    @classmethod
+    def create(cls, devices, coarse, codebooks, perm=None, R=None, clamp=1.0):
+        coarse, codebooks = _f32(coarse), _f32(codebooks)
+        K, D = coarse.shape
+        M, ksub, ds = codebooks.shape
+        perm_a = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        R_a = None if R is None else _f32(R)
+        d, nd = cls._devs(devices)
+        h = C.c_void_p()
+        _check(load().b200nn_mpq_create(_vp(d), nd, C.c_int(D), C.c_int(K), C.c_int(M), C.c_int(ksub), _vp(coarse), _vp(codebooks), _vp(perm_a),
+                                        _vp(R_a), C.c_float(clamp), C.byref(h)), "mpq_create")
+        return cls(h)
+
+    @classmethod
+    def load_model(cls, devices, path: str):
+        d, nd = cls._devs(devices)
+        h = C.c_void_p()
+        _check(load().b200nn_mpq_load_model(_vp(d), nd, path.encode(), C.byref(h)), "mpq_load_model")
+        return cls(h)
+
+    @classmethod
+    def load_index(cls, devices, path: str, perm=None, clamp=1.0):
+        d, nd = cls._devs(devices)
+        perm_a = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        h = C.c_void_p()
+        _check(load().b200nn_mpq_load_index(_vp(d), nd, path.encode(), _vp(perm_a), C.c_float(clamp), C.byref(h)), "mpq_load_index")
+        return cls(h)
+
+    def close(self):
+        if self.h:
+            load().b200nn_mpq_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _info64(self):
+        n, g = C.c_uint64(), C.c_uint64()
+        _check(load().b200nn_mpq_info(self.h, None, None, None, None, C.byref(n), C.byref(g), None, None), "mpq_info")
+        return int(n.value), int(g.value)
+
+    @property
+    def n_rows(self):
+        return self._info64()[0]
+
+    @property
+    def n_groups(self):
+        return self._info64()[1]
+
+    def shard_rows(self):
+        r = np.zeros(self.n_devices, dtype=np.uint64)
+        _check(load().b200nn_mpq_shard_rows(self.h, _vp(r)), "mpq_shard_rows")
+        return r.astype(np.int64)
+
+    def set_clamp(self, clamp: float):
+        _check(load().b200nn_mpq_set_clamp(self.h, C.c_float(clamp)), "mpq_set_clamp")
+
+    def add(self, x_raw, group_ids=None):
+        x_raw = _f32(x_raw)
+        g = None if group_ids is None else np.ascontiguousarray(group_ids, dtype=np.int32)
+        _check(load().b200nn_mpq_add(self.h, _vp(x_raw), C.c_size_t(x_raw.shape[0]), _vp(g)), "mpq_add")
+
+    def search(self, q_raw, k, nprobe=1):
+        q_raw = _f32(q_raw)
+        nq = q_raw.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.uint64)
+        _check(load().b200nn_mpq_search(self.h, _vp(q_raw), C.c_size_t(nq), C.c_int(nprobe), C.c_size_t(k), _vp(D), _vp(I)), "mpq_search")
+        return D, I
+
+    def search_host_ptr(self, q_ptr: int, nq: int, k: int, nprobe: int, out_dist_ptr: int, out_id_ptr: int):
+        _check(load().b200nn_mpq_search(self.h, C.c_void_p(q_ptr), C.c_size_t(nq), C.c_int(nprobe), C.c_size_t(k), C.c_void_p(out_dist_ptr),
+                                        C.c_void_p(out_id_ptr)), "mpq_search")
+
+    def scores(self, q_raw, nprobe=3):
+        q_raw = _f32(q_raw)
+        out = np.empty((q_raw.shape[0], self.n_groups), dtype=np.float32)
+        _check(load().b200nn_mpq_scores(self.h, _vp(q_raw), C.c_size_t(q_raw.shape[0]), C.c_int(nprobe), _vp(out)), "mpq_scores")
+        return out
+
+    def save_index(self, dir_or_path: str, group_paths=None):
+        arr, n = None, 0
+        if group_paths is not None:
+            arr = (C.c_char_p * len(group_paths))(*[p.encode() for p in group_paths])
+            n = len(group_paths)
+        _check(load().b200nn_mpq_save_index(self.h, dir_or_path.encode(), arr, C.c_size_t(n)), "mpq_save_index")
 
 
 class FlatIndex:
@@ -308,6 +477,21 @@ class FlatIndex:
         _check(load().b200nn_flat_load(ctx.h, C.c_int(cls.METRIC[metric]), C.c_int(order), C.c_size_t(dim), path.encode(),
                                        C.byref(h)), "flat_load")
         return cls(ctx, metric, dim, 0, order, _handle=h)
+
+    @classmethod
+    def load_hnsw_file(cls, ctx, metric: str, dim: int, path: str, order: int = 4):
+        """vectors + labels of a HierarchicalNSW::saveIndex file as an exact flat index (hnswalg.h:491-519)."""
+        h = C.c_void_p()
+        _check(load().b200nn_flat_load_hnsw(ctx.h, C.c_int(cls.METRIC[metric]), C.c_int(order), C.c_size_t(dim), path.encode(),
+                                            C.byref(h)), "flat_load_hnsw")
+        return cls(ctx, metric, dim, 0, order, _handle=h)
+
+    def info(self):
+        mx, n = C.c_size_t(), C.c_size_t()
+        _check(load().b200nn_flat_info(self.h, C.byref(mx), C.byref(n), None, C.c_size_t(0)), "flat_info")
+        labels = np.zeros(n.value, dtype=np.uint64)
+        _check(load().b200nn_flat_info(self.h, None, None, _vp(labels), C.c_size_t(labels.shape[0])), "flat_info")
+        return int(mx.value), int(n.value), labels
 
     def close(self):
         if self.h:

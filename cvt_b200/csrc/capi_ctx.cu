@@ -54,6 +54,8 @@ void b200nn_ctx_destroy(b200nn_ctx_t ctx) {
 
 int b200nn_ctx_set_stream(b200nn_ctx_t ctx, void* cuda_stream) {
     if (!ctx) B2_FAIL(B200NN_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    B2_CUDA(cudaSetDevice(ctx->c.device));
     B2_CUDA(cudaStreamSynchronize(ctx->c.stream));
     ctx->c.stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->c.own_stream;
     return 0;
@@ -74,12 +76,16 @@ int b200nn_ctx_launch_count(b200nn_ctx_t ctx, uint64_t* out) {
 
 int b200nn_ctx_event_record(b200nn_ctx_t ctx, int slot) {
     if (!ctx || slot < 0 || slot >= 8) B2_FAIL(B200NN_ERR_INVALID, "event slot must be in [0,8)");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    B2_CUDA(cudaSetDevice(ctx->c.device));
     B2_CUDA(cudaEventRecord(ctx->c.events[8 + slot], ctx->c.stream));
     return 0;
 }
 
 int b200nn_ctx_event_elapsed_ms(b200nn_ctx_t ctx, int a, int b, float* ms) {
     if (!ctx || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) B2_FAIL(B200NN_ERR_INVALID, "bad event slot");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    B2_CUDA(cudaSetDevice(ctx->c.device));
     B2_CUDA(cudaEventSynchronize(ctx->c.events[8 + b]));
     B2_CUDA(cudaEventElapsedTime(ms, ctx->c.events[8 + a], ctx->c.events[8 + b]));
     return 0;

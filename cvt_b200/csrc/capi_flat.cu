@@ -291,4 +291,68 @@ int b200nn_flat_load(b200nn_ctx_t ctx, int metric, int order, size_t dim, const 
     return rc;
 }
 
+// The index file of hnswlib::HierarchicalNSW<dist_t>::saveIndex (hnsw_sifts_retrieval/hnswlib/hnswalg.h:491-519), the file
+// hnsw_sifts_retrieval/makeSearch.cpp:19-22 / siftsIndex.cpp:5-7 open: header {size_t offsetLevel0, max_elements,
+// cur_element_count, size_data_per_element, label_offset, offsetData; int maxlevel; unsigned enterpoint; size_t maxM, maxM0,
+// M; double mult; size_t ef_construction}, then max_elements x size_data_per_element bytes of level-0 memory where element i
+// is [links | vector at offsetData | size_t label at label_offset]; the upper-level link lists follow and are skipped --
+// the exact scan needs the vectors and labels only.  The graph is NOT rebuilt: searchKnn over this index is exact.
+int b200nn_flat_load_hnsw(b200nn_ctx_t ctx, int metric, int order, size_t dim, const char* path, b200nn_flat_t* out) {
+    if (!ctx || !path || !out) B2_FAIL(B200NN_ERR_INVALID, "flat_load_hnsw: NULL argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) B2_FAIL(B200NN_ERR_IO, std::string("flat_load_hnsw: cannot open ") + path);
+    auto bad = [&](const char* msg) { fclose(f); B2_FAIL(B200NN_ERR_IO, msg); };
+    size_t h6[6];
+    int maxlevel;
+    unsigned enter;
+    size_t m3[3], efc;
+    double mult;
+    if (fread(h6, sizeof(size_t), 6, f) != 6 || fread(&maxlevel, 4, 1, f) != 1 || fread(&enter, 4, 1, f) != 1 ||
+        fread(m3, sizeof(size_t), 3, f) != 3 || fread(&mult, 8, 1, f) != 1 || fread(&efc, sizeof(size_t), 1, f) != 1)
+        return bad("flat_load_hnsw: truncated header");
+    const size_t off0 = h6[0], max_el = h6[1], cur = h6[2], spe = h6[3], label_off = h6[4], off_data = h6[5];
+    const size_t row_bytes = metric == 2 ? dim : dim * 4;
+    // hnswalg.h:39-44: size_links_level0 = maxM0*4 + 4; size_data_per_element = links + data + label; offsetData = links
+    if (off0 != 0 || cur > max_el || label_off != off_data + row_bytes || spe != label_off + sizeof(size_t) ||
+        off_data != m3[1] * sizeof(unsigned) + sizeof(unsigned) || max_el >= 0xFFFFFFFFull)
+        return bad("flat_load_hnsw: not a HierarchicalNSW index of this metric/dimension");
+    int rc = flat_new(ctx, metric, order, dim, max_el, out);
+    if (rc) { fclose(f); return rc; }
+    const size_t blk = 16384;
+    std::vector<unsigned char> raw(blk * spe), rows(blk * row_bytes);
+    std::vector<uint64_t> labels(blk);
+    for (size_t i0 = 0; i0 < cur; i0 += blk) {
+        const size_t cn = std::min(blk, cur - i0);
+        if (fread(raw.data(), spe, cn, f) != cn) { b200nn_flat_destroy(*out); *out = nullptr; return bad("flat_load_hnsw: truncated level-0 memory"); }
+        for (size_t i = 0; i < cn; i++) {
+            memcpy(rows.data() + i * row_bytes, raw.data() + i * spe + off_data, row_bytes);
+            size_t lab;
+            memcpy(&lab, raw.data() + i * spe + label_off, sizeof(size_t));
+            labels[i] = lab;
+        }
+        if ((rc = b200nn_flat_add(*out, rows.data(), labels.data(), cn))) {
+            fclose(f);
+            b200nn_flat_destroy(*out);
+            *out = nullptr;
+            return rc;
+        }
+    }
+    fclose(f);
+    return 0;
+}
+
+/* capacity and labels of an index (row order) -- what a loaded index has to tell its host-side wrapper */
+int b200nn_flat_info(b200nn_flat_t p, size_t* max_elements, size_t* n, uint64_t* labels_out, size_t labels_capacity) {
+    if (!p) B2_FAIL(B200NN_ERR_INVALID, "flat is NULL");
+    FGuard g(p);
+    if (max_elements) *max_elements = p->max_elements;
+    if (n) *n = p->n;
+    if (labels_out) {
+        if (labels_capacity < p->n) B2_FAIL(B200NN_ERR_INVALID, "flat_info: labels buffer too small");
+        std::copy(p->labels.begin(), p->labels.end(), labels_out);
+    }
+    return 0;
+}
+
 }  // extern "C"

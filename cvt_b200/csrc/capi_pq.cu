@@ -7,6 +7,7 @@
 #include <string>
 
 #include "capi_common.cuh"
+#include "capi_pq_internal.cuh"
 #include "pq_kernels.cuh"
 #include "rotate_gemm.cuh"
 #include "topk.cuh"
@@ -316,6 +317,141 @@ int search_dev_locked(b200nn_pq* p, const float* q_raw_dev, long long nq, int np
 
 }  // namespace
 
+// ---- host-side pieces shared with the multi-GPU layer (capi_pq_internal.cuh) -----------------------------------
+std::string pq_index_file_name(const char* dir_or_path, long long n_groups, int D, int K, int M, int ksub) {
+    std::string path = dir_or_path;
+    if (path.size() < 6 || path.substr(path.size() - 6) != ".fvecs")
+        path += "/OPQ_Index_db_" + std::to_string(n_groups) + "_dim_" + std::to_string(D) + "_k_" + std::to_string(K) + "_PQ_m" +
+                std::to_string(M) + "_k" + std::to_string(ksub) + ".fvecs";
+    return path;
+}
+
+int pq_model_to_host(b200nn_pq_t p, std::vector<float>* coarse, std::vector<float>* cb, std::vector<int>* perm) {
+    Guard g(p);
+    Ctx* c = &p->ctx->c;
+    if (coarse) {
+        coarse->resize((size_t)p->K * p->D);
+        B2_CUDA(cudaMemcpyAsync(coarse->data(), p->coarse.p, sizeof(float) * coarse->size(), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (cb) {
+        cb->resize((size_t)p->M * p->ksub * p->ds);
+        B2_CUDA(cudaMemcpyAsync(cb->data(), p->cb.p, sizeof(float) * cb->size(), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (perm) {
+        perm->clear();
+        if (p->has_perm) {
+            perm->resize(p->D);
+            B2_CUDA(cudaMemcpyAsync(perm->data(), p->perm.p, sizeof(int) * p->D, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pq_rows_to_host(b200nn_pq_t p, PQHostRows* rows) {
+    Guard g(p);
+    Ctx* c = &p->ctx->c;
+    const size_t n = (size_t)p->n;
+    rows->lists.resize(n);
+    rows->groups.resize(n);
+    rows->codes.resize(n * p->M);
+    if (n) {
+        B2_CUDA(cudaMemcpyAsync(rows->lists.data(), p->list.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA(cudaMemcpyAsync(rows->groups.data(), p->group.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA(cudaMemcpyAsync(rows->codes.data(), p->codes.p, n * p->M, cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+// rows in insertion order -> the reference's file: per coarse list, elements in insertion order (IVFOPQ.cpp:541-580)
+int pq_write_index_file(const std::string& path, int D, int K, int M, int ksub, long long n_groups, const float* coarse, const float* cb,
+                        long long n, const int* lists, const int* groups, const unsigned char* codes, const char* const* group_paths,
+                        size_t n_paths) {
+    std::vector<long long> off((size_t)K + 1, 0);
+    for (long long i = 0; i < n; i++) {
+        if (lists[i] < 0 || lists[i] >= K) B2_FAIL(B200NN_ERR_STATE, "index holds a row with an invalid coarse list id");
+        off[lists[i] + 1]++;
+    }
+    for (int k = 0; k < K; k++) off[k + 1] += off[k];
+    std::vector<long long> order((size_t)n), cur(off.begin(), off.end() - 1);
+    for (long long i = 0; i < n; i++) order[cur[lists[i]]++] = i;  // stable
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) B2_FAIL(B200NN_ERR_IO, "pq_save_index: cannot open " + path);
+    const int32_t h[5] = {D, K, M, ksub, (int32_t)n_groups};
+    fwrite(h, 4, 5, f);
+    fwrite(coarse, 4, (size_t)K * D, f);
+    fwrite(cb, 4, (size_t)M * ksub * (D / M), f);
+    std::vector<unsigned char> blk;
+    for (int k = 0; k < K; k++) {
+        const int32_t cnt = (int32_t)(off[k + 1] - off[k]);
+        fwrite(&cnt, 4, 1, f);
+        blk.resize((size_t)cnt * (4 + M));
+        for (long long r = off[k]; r < off[k + 1]; r++) {
+            unsigned char* d = blk.data() + (size_t)(r - off[k]) * (4 + M);
+            memcpy(d, &groups[order[r]], 4);
+            memcpy(d + 4, codes + (size_t)order[r] * M, M);
+        }
+        if (cnt) fwrite(blk.data(), 1, blk.size(), f);
+    }
+    char name[260];
+    for (long long i = 0; i < n_groups; i++) {
+        memset(name, 0, sizeof name);
+        if (group_paths && (size_t)i < n_paths && group_paths[i]) strncpy(name, group_paths[i], 259);
+        fwrite(name, 1, 260, f);
+    }
+    const bool ok = !ferror(f);
+    fclose(f);
+    if (!ok) B2_FAIL(B200NN_ERR_IO, "pq_save_index: write failed");
+    return 0;
+}
+
+// The file is untrusted input: every id and code byte is checked before it can index device memory.
+int pq_parse_index_file(const char* path, int* D_, int* K_, int* M_, int* ksub_, long long* ng_, std::vector<float>* coarse,
+                        std::vector<float>* cb, PQHostRows* rows) {
+    FILE* f = fopen(path, "rb");
+    if (!f) B2_FAIL(B200NN_ERR_IO, "Can not open the index file.");  // IVFOPQ.cpp:470
+    auto bad = [&](const char* msg) { fclose(f); B2_FAIL(B200NN_ERR_IO, msg); };
+    int32_t h[5];
+    if (fread(h, 4, 5, f) != 5) return bad("pq_load_index: truncated header");
+    const int D = h[0], K = h[1], M = h[2], ksub = h[3];
+    const long long ng = h[4];
+    if (D <= 0 || K <= 0 || M <= 0 || ksub <= 0 || ksub > 256 || D % M || ng < 0 || (long long)K * D > (1LL << 32))
+        return bad("pq_load_index: implausible header");
+    coarse->resize((size_t)K * D);
+    cb->resize((size_t)M * ksub * (D / M));
+    if (fread(coarse->data(), 4, coarse->size(), f) != coarse->size() || fread(cb->data(), 4, cb->size(), f) != cb->size())
+        return bad("pq_load_index: truncated model section");
+    std::vector<unsigned char> blk;
+    const size_t rec = 4 + (size_t)M;  // int32 videoId + M code bytes per element (IVFOPQ.cpp:569-573)
+    rows->lists.clear(); rows->groups.clear(); rows->codes.clear();
+    for (int k = 0; k < K; k++) {
+        int32_t cnt = 0;
+        if (fread(&cnt, 4, 1, f) != 1 || cnt < 0) return bad("pq_load_index: truncated list section");
+        if (rows->lists.size() + (size_t)cnt > 0x7fffffffull) return bad("pq_load_index: more than 2^31-1 rows");
+        blk.resize((size_t)cnt * rec);
+        if (cnt && fread(blk.data(), rec, (size_t)cnt, f) != (size_t)cnt) return bad("pq_load_index: truncated element");
+        const size_t base = rows->lists.size();
+        rows->lists.resize(base + cnt, k);
+        rows->groups.resize(base + cnt);
+        rows->codes.resize((base + cnt) * (size_t)M);
+        for (size_t j = 0; j < (size_t)cnt; j++) {
+            int32_t gid;
+            memcpy(&gid, blk.data() + j * rec, 4);
+            if (gid < 0) return bad("pq_load_index: negative group id in the index file");
+            rows->groups[base + j] = gid;
+            const unsigned char* cj = blk.data() + j * rec + 4;
+            if (ksub < 256)
+                for (int m = 0; m < M; m++)
+                    if (cj[m] >= ksub) return bad("pq_load_index: code byte >= ksub in the index file");
+            memcpy(rows->codes.data() + (base + j) * M, cj, M);
+        }
+    }
+    fclose(f);
+    *D_ = D; *K_ = K; *M_ = M; *ksub_ = ksub; *ng_ = ng;
+    return 0;
+}
+
 extern "C" {
 
 int b200nn_pq_create(b200nn_ctx_t ctx, int D, int K, int M, int ksub, const float* coarse, const float* codebooks,
@@ -471,7 +607,33 @@ int b200nn_pq_build_lut(b200nn_pq_t p, const float* q_rot, size_t nq, int nprobe
     return 0;
 }
 
-// IVFOPQ::QueryThrehold (IVFOPQ.cpp:322-422) for nq raw query rows: clamp-initialised, min per group.
+// IVFOPQ::QueryThrehold (IVFOPQ.cpp:322-422) for nq raw DEVICE query rows: out[q][g] (row stride out_stride >= n_groups)
+// is initialised to the clamp value and min-aggregated per group over the probed lists.  Workspaces must hold nq queries.
+static int scores_dev_locked(b200nn_pq* p, const float* q_raw_dev, long long nq, int nprobe, long long out_stride, float* out_dev) {
+    Ctx* c = &p->ctx->c;
+    int rc;
+    if ((rc = ensure_csr(p))) return rc;
+    if ((rc = p->ws_q.ensure((size_t)nq * p->D)) || (rc = p->ws_probes.ensure((size_t)nq * nprobe)) ||
+        (rc = p->ws_lut.ensure((size_t)nq * nprobe * p->M * p->ksub)))
+        return rc;
+    const float* qr = nullptr;
+    if ((rc = rotate_dev(p, q_raw_dev, nq, p->ws_q.p, &qr))) return rc;
+    if ((rc = probes_and_luts(p, qr, nq, nprobe, p->ws_probes.p, p->ws_lut.p))) return rc;
+    if ((rc = launch_fill_f32(c, out_dev, nq * out_stride, p->clamp))) return rc;
+    if (p->n == 0) return 0;
+    return launch_ivf_scan(c, p->ws_lut.p, p->ws_probes.p, p->list_off.p, p->codes_sorted.p, p->group_sorted.p, p->M, p->ksub, nq, nprobe,
+                           out_stride, out_dev);
+}
+
+int b200nn_pq_scores_dev(b200nn_pq_t p, const float* q_raw_dev, size_t nq, int nprobe, size_t out_stride, float* out_scores_dev) {
+    if (!p || (nq && (!q_raw_dev || !out_scores_dev))) B2_FAIL(B200NN_ERR_INVALID, "pq_scores_dev: NULL argument");
+    if (nprobe < 1 || nprobe > p->K) B2_FAIL(B200NN_ERR_INVALID, "pq_scores_dev: nprobe must be in [1, K]");
+    if (out_stride < (size_t)p->n_groups) B2_FAIL(B200NN_ERR_INVALID, "pq_scores_dev: out_stride is smaller than the number of groups");
+    if (!nq || !out_stride) return 0;
+    Guard g(p);
+    return scores_dev_locked(p, q_raw_dev, (long long)nq, nprobe, (long long)out_stride, out_scores_dev);
+}
+
 int b200nn_pq_scores(b200nn_pq_t p, const float* q_raw, size_t nq, int nprobe, float* out_scores) {
     if (!p || (nq && (!q_raw || !out_scores))) B2_FAIL(B200NN_ERR_INVALID, "pq_scores: NULL argument");
     if (nprobe < 1 || nprobe > p->K) B2_FAIL(B200NN_ERR_INVALID, "pq_scores: nprobe must be in [1, K]");
@@ -479,23 +641,13 @@ int b200nn_pq_scores(b200nn_pq_t p, const float* q_raw, size_t nq, int nprobe, f
     Guard g(p);
     Ctx* c = &p->ctx->c;
     int rc;
-    if ((rc = ensure_csr(p))) return rc;
     const long long ng = p->n_groups;
     const long long qc = std::max<long long>(1, std::min<long long>((long long)nq, std::min<long long>(1024, (1LL << 28) / ng)));
-    if ((rc = p->ws_qraw.ensure((size_t)qc * p->D)) || (rc = p->ws_q.ensure((size_t)qc * p->D)) ||
-        (rc = p->ws_probes.ensure((size_t)qc * nprobe)) || (rc = p->ws_lut.ensure((size_t)qc * nprobe * p->M * p->ksub)) ||
-        (rc = p->ws_scores.ensure((size_t)qc * ng)))
-        return rc;
+    if ((rc = p->ws_qraw.ensure((size_t)qc * p->D)) || (rc = p->ws_scores.ensure((size_t)qc * ng))) return rc;
     for (long long q0 = 0; q0 < (long long)nq; q0 += qc) {
         const long long cq = std::min<long long>(qc, (long long)nq - q0);
         B2_CUDA(cudaMemcpyAsync(p->ws_qraw.p, q_raw + q0 * p->D, sizeof(float) * cq * p->D, cudaMemcpyHostToDevice, c->stream));
-        const float* qr = nullptr;
-        if ((rc = rotate_dev(p, p->ws_qraw.p, cq, p->ws_q.p, &qr))) return rc;
-        if ((rc = probes_and_luts(p, qr, cq, nprobe, p->ws_probes.p, p->ws_lut.p))) return rc;
-        if ((rc = launch_fill_f32(c, p->ws_scores.p, cq * ng, p->clamp))) return rc;
-        if ((rc = launch_ivf_scan(c, p->ws_lut.p, p->ws_probes.p, p->list_off.p, p->codes_sorted.p, p->group_sorted.p, p->M, p->ksub,
-                                  cq, nprobe, ng, p->ws_scores.p)))
-            return rc;
+        if ((rc = scores_dev_locked(p, p->ws_qraw.p, cq, nprobe, ng, p->ws_scores.p))) return rc;
         B2_CUDA(cudaMemcpyAsync(out_scores + q0 * ng, p->ws_scores.p, sizeof(float) * cq * ng, cudaMemcpyDeviceToHost, c->stream));
         B2_CUDA(cudaStreamSynchronize(c->stream));
     }
@@ -617,49 +769,55 @@ int b200nn_pq_scan_plan(int sm_count, int M, size_t nq, size_t n_rows, int* n_fu
 // IVFOPQ::SaveIndex byte format (IVFOPQ.cpp:541-580).  `dir_or_path` ending in
 // ".fvecs" is used verbatim, otherwise the reference's file name is composed inside that directory.
 int b200nn_pq_save_index(b200nn_pq_t p, const char* dir_or_path, const char* const* group_paths) {
+    return b200nn_pq_save_index_n(p, dir_or_path, group_paths, group_paths ? (size_t)-1 : 0);
+}
+
+int b200nn_pq_save_index_n(b200nn_pq_t p, const char* dir_or_path, const char* const* group_paths, size_t n_paths) {
     if (!p || !dir_or_path) B2_FAIL(B200NN_ERR_INVALID, "pq_save_index: NULL argument");
+    std::vector<float> coarse, cb;
+    PQHostRows rows;
+    int rc;
+    if ((rc = pq_model_to_host(p, &coarse, &cb, nullptr)) || (rc = pq_rows_to_host(p, &rows))) return rc;
+    return pq_write_index_file(pq_index_file_name(dir_or_path, p->n_groups, p->D, p->K, p->M, p->ksub), p->D, p->K, p->M, p->ksub,
+                               p->n_groups, coarse.data(), cb.data(), (long long)rows.lists.size(), rows.lists.data(), rows.groups.data(),
+                               rows.codes.data(), group_paths, n_paths);
+}
+
+// Append rows that are already coded (host pointers): coarse list id, videoId and M code bytes per row -- what an index
+// file holds.  Every value is validated before it can index device memory.
+int b200nn_pq_append_coded(b200nn_pq_t p, const int32_t* lists, const int32_t* group_ids, const uint8_t* codes, size_t n) {
+    if (!p || (n && (!lists || !codes))) B2_FAIL(B200NN_ERR_INVALID, "pq_append_coded: NULL argument");
+    if (!n) return 0;
+    if ((unsigned long long)p->n + n > 0x7fffffffull) B2_FAIL(B200NN_ERR_STATE, "pq_append_coded: more than 2^31-1 rows per shard");
+    long long ng = p->n_groups;
+    for (size_t i = 0; i < n; i++) {
+        if (lists[i] < 0 || lists[i] >= p->K) B2_FAIL(B200NN_ERR_INVALID, "pq_append_coded: coarse list id out of range");
+        if (group_ids && group_ids[i] < 0) B2_FAIL(B200NN_ERR_INVALID, "pq_append_coded: negative group id");
+        if (group_ids) ng = std::max<long long>(ng, (long long)group_ids[i] + 1);
+        if (p->ksub < 256)
+            for (int m = 0; m < p->M; m++)
+                if (codes[i * p->M + m] >= p->ksub) B2_FAIL(B200NN_ERR_INVALID, "pq_append_coded: code byte >= ksub");
+    }
     Guard g(p);
     Ctx* c = &p->ctx->c;
     int rc;
-    if ((rc = ensure_csr(p))) return rc;
-    std::string path = dir_or_path;
-    if (path.size() < 6 || path.substr(path.size() - 6) != ".fvecs")
-        path += "/OPQ_Index_db_" + std::to_string(p->n_groups) + "_dim_" + std::to_string(p->D) + "_k_" + std::to_string(p->K) +
-                "_PQ_m" + std::to_string(p->M) + "_k" + std::to_string(p->ksub) + ".fvecs";
-    const long long n = p->n;
-    std::vector<unsigned char> codes((size_t)n * p->M);
-    std::vector<int> grp(n);
-    std::vector<long long> off(p->K + 1);
-    std::vector<float> coarse((size_t)p->K * p->D), cb((size_t)p->M * p->ksub * p->ds);
-    B2_CUDA(cudaMemcpyAsync(codes.data(), p->codes_sorted.p, codes.size(), cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaMemcpyAsync(grp.data(), p->group_sorted.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaMemcpyAsync(off.data(), p->list_off.p, sizeof(long long) * (p->K + 1), cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaMemcpyAsync(coarse.data(), p->coarse.p, sizeof(float) * coarse.size(), cudaMemcpyDeviceToHost, c->stream));
-    B2_CUDA(cudaMemcpyAsync(cb.data(), p->cb.p, sizeof(float) * cb.size(), cudaMemcpyDeviceToHost, c->stream));
+    const size_t n0 = (size_t)p->n;
+    if ((rc = p->codes.reserve((n0 + n) * p->M, n0 * p->M, c->stream)) || (rc = p->list.reserve(n0 + n, n0, c->stream)) ||
+        (rc = p->group.reserve(n0 + n, n0, c->stream)))
+        return rc;
+    B2_CUDA(cudaMemcpyAsync(p->codes.p + n0 * p->M, codes, n * p->M, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaMemcpyAsync(p->list.p + n0, lists, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    if (group_ids) B2_CUDA(cudaMemcpyAsync(p->group.p + n0, group_ids, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    else {
+        iota_kernel<<<small_grid((long long)n), 256, 0, c->stream>>>(p->group.p + n0, (long long)n, (int)n0);
+        c->launches++;
+        ng = std::max<long long>(ng, (long long)(n0 + n));
+    }
     B2_CUDA(cudaStreamSynchronize(c->stream));
-    FILE* f = fopen(path.c_str(), "wb");
-    if (!f) B2_FAIL(B200NN_ERR_IO, "pq_save_index: cannot open " + path);
-    const int32_t h[5] = {p->D, p->K, p->M, p->ksub, (int32_t)p->n_groups};
-    fwrite(h, 4, 5, f);
-    fwrite(coarse.data(), 4, coarse.size(), f);
-    fwrite(cb.data(), 4, cb.size(), f);
-    for (int k = 0; k < p->K; k++) {
-        const int32_t cnt = (int32_t)(off[k + 1] - off[k]);
-        fwrite(&cnt, 4, 1, f);
-        for (long long r = off[k]; r < off[k + 1]; r++) {
-            fwrite(&grp[r], 4, 1, f);
-            fwrite(&codes[(size_t)r * p->M], 1, p->M, f);
-        }
-    }
-    char name[260];
-    for (long long i = 0; i < p->n_groups; i++) {
-        memset(name, 0, sizeof name);
-        if (group_paths && group_paths[i]) strncpy(name, group_paths[i], 259);
-        fwrite(name, 1, 260, f);
-    }
-    const bool ok = !ferror(f);
-    fclose(f);
-    if (!ok) B2_FAIL(B200NN_ERR_IO, "pq_save_index: write failed");
+    p->n += (long long)n;
+    p->n_groups = ng;
+    p->codesT_rows = -1;
+    p->csr_rows = -1;
     return 0;
 }
 
@@ -667,56 +825,21 @@ int b200nn_pq_save_index(b200nn_pq_t p, const char* dir_or_path, const char* con
 // SURVEY.md App. D-2).  The file has no reorder tail, so perm comes from the caller (may be NULL).
 int b200nn_pq_load_index(b200nn_ctx_t ctx, const char* path, const int32_t* perm, float clamp, b200nn_pq_t* out) {
     if (!ctx || !path || !out) B2_FAIL(B200NN_ERR_INVALID, "pq_load_index: NULL argument");
-    FILE* f = fopen(path, "rb");
-    if (!f) B2_FAIL(B200NN_ERR_IO, "Can not open the index file.");  // IVFOPQ.cpp:470
-    int32_t h[5];
-    if (fread(h, 4, 5, f) != 5) { fclose(f); B2_FAIL(B200NN_ERR_IO, "pq_load_index: truncated header"); }
-    const int D = h[0], K = h[1], M = h[2], ksub = h[3];
-    const long long ng = h[4];
-    if (D <= 0 || K <= 0 || M <= 0 || ksub <= 0 || D % M || ng < 0) { fclose(f); B2_FAIL(B200NN_ERR_IO, "pq_load_index: implausible header"); }
-    std::vector<float> coarse((size_t)K * D), cb((size_t)M * ksub * (D / M));
-    if (fread(coarse.data(), 4, coarse.size(), f) != coarse.size() || fread(cb.data(), 4, cb.size(), f) != cb.size()) {
-        fclose(f);
-        B2_FAIL(B200NN_ERR_IO, "pq_load_index: truncated model section");
+    *out = nullptr;
+    int D, K, M, ksub;
+    long long ng;
+    std::vector<float> coarse, cb;
+    PQHostRows rows;
+    int rc;
+    if ((rc = pq_parse_index_file(path, &D, &K, &M, &ksub, &ng, &coarse, &cb, &rows))) return rc;
+    b200nn_pq* p = nullptr;
+    if ((rc = pq_init(ctx, D, K, M, ksub, coarse.data(), cb.data(), perm, nullptr, clamp, &p))) return rc;
+    if ((rc = b200nn_pq_append_coded(p, rows.lists.data(), rows.groups.data(), rows.codes.data(), rows.lists.size()))) {
+        b200nn_pq_destroy(p);  // no half-built handle escapes
+        return rc;
     }
-    std::vector<int> lists, groups;
-    std::vector<unsigned char> codes, blk;
-    const size_t rec = 4 + (size_t)M;  // int32 videoId + M code bytes per element (IVFOPQ.cpp:569-573)
-    for (int k = 0; k < K; k++) {
-        int32_t cnt = 0;
-        if (fread(&cnt, 4, 1, f) != 1 || cnt < 0) { fclose(f); B2_FAIL(B200NN_ERR_IO, "pq_load_index: truncated list section"); }
-        blk.resize((size_t)cnt * rec);
-        if (cnt && fread(blk.data(), rec, (size_t)cnt, f) != (size_t)cnt) { fclose(f); B2_FAIL(B200NN_ERR_IO, "pq_load_index: truncated element"); }
-        const size_t base = lists.size();
-        lists.resize(base + cnt, k);
-        groups.resize(base + cnt);
-        codes.resize((base + cnt) * (size_t)M);
-        for (size_t j = 0; j < (size_t)cnt; j++) {
-            int32_t gid;
-            memcpy(&gid, blk.data() + j * rec, 4);
-            groups[base + j] = gid;
-            memcpy(codes.data() + (base + j) * M, blk.data() + j * rec + 4, M);
-        }
-    }
-    fclose(f);
-    int rc = pq_init(ctx, D, K, M, ksub, coarse.data(), cb.data(), perm, nullptr, clamp, out);
-    if (rc) return rc;
-    b200nn_pq* p = *out;
-    Guard g(p);
-    Ctx* c = &ctx->c;
-    const long long n = (long long)lists.size();
-    if (n) {
-        if ((rc = p->codes.reserve((size_t)n * M, 0, c->stream)) || (rc = p->list.reserve(n, 0, c->stream)) ||
-            (rc = p->group.reserve(n, 0, c->stream)))
-            return rc;
-        B2_CUDA(cudaMemcpyAsync(p->codes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice, c->stream));
-        B2_CUDA(cudaMemcpyAsync(p->list.p, lists.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-        B2_CUDA(cudaMemcpyAsync(p->group.p, groups.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-        B2_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    p->n = n;
-    p->n_groups = ng;
-    for (long long i = 0; i < n; i++) p->n_groups = std::max<long long>(p->n_groups, (long long)groups[i] + 1);
+    p->n_groups = std::max<long long>(p->n_groups, ng);
+    *out = p;
     return 0;
 }
 

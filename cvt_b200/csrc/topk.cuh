@@ -91,4 +91,8 @@ __device__ __forceinline__ float tau_f32_of(unsigned long long tkey) {
 int launch_topk_merge(Ctx* ctx, const unsigned long long* keys, int L, long long nq, int k, long long list_stride,
                       float* out_dist_f, int* out_dist_i, unsigned long long* out_id, unsigned long long* out_key);
 
+// the same merge with the L lists given as L device pointers ([nq][k] each; may point into peer GPUs' memory)
+int launch_topk_merge_ptrs(Ctx* ctx, const unsigned long long* const* list_ptrs_dev, int L, long long nq, int k, float* out_dist_f,
+                           int* out_dist_i, unsigned long long* out_id, unsigned long long* out_key);
+
 }  // namespace b200nn

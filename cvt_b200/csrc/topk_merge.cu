@@ -11,19 +11,28 @@ namespace b200nn {
 // are the all-gathered records of a (query chunk x row shard) grid of ranks.  Missing results (fewer
 // than k real records) are written as (+inf | INT32_MAX, UINT64_MAX).
 // ---------------------------------------------------------------------------------------------
-__global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, int L, long long nq, int k,
-                                  long long list_stride, float* __restrict__ out_dist_f, int* __restrict__ out_dist_i,
+// ptrs != nullptr: list l of query q starts at ptrs[l] + q*k instead -- the lists may then live in the memory of OTHER
+// GPUs (peer access over NVLink): the gather of the shards' candidates and their merge are this one kernel.
+__global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* const* __restrict__ ptrs, int L,
+                                  long long nq, int k, long long list_stride, float* __restrict__ out_dist_f, int* __restrict__ out_dist_i,
                                   unsigned long long* __restrict__ out_id, unsigned long long* __restrict__ out_key) {
     extern __shared__ unsigned long long s_keys[];  // [warps][L*k]: the query's lists, staged once
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + w;
     if (q >= nq) return;
     unsigned long long* sk = s_keys + (size_t)w * L * k;
-    const long long cq = list_stride / k, chunk = q / cq;
-    const unsigned long long* base = keys + (chunk * (L - 1) * cq + q) * k;  // = ((chunk*L)*cq + (q - chunk*cq)) * k
-    for (int e = lane; e < L * k; e += 32) {
-        const int l = e / k, j = e - l * k;
-        sk[e] = base[(long long)l * list_stride + j];
+    if (ptrs) {
+        for (int e = lane; e < L * k; e += 32) {
+            const int l = e / k, j = e - l * k;
+            sk[e] = ptrs[l][q * k + j];
+        }
+    } else {
+        const long long cq = list_stride / k, chunk = q / cq;
+        const unsigned long long* base = keys + (chunk * (L - 1) * cq + q) * k;  // = ((chunk*L)*cq + (q - chunk*cq)) * k
+        for (int e = lane; e < L * k; e += 32) {
+            const int l = e / k, j = e - l * k;
+            sk[e] = base[(long long)l * list_stride + j];
+        }
     }
     __syncwarp();
     int real = 0;
@@ -130,7 +139,22 @@ int launch_topk_merge(Ctx* ctx, const unsigned long long* keys, int L, long long
     if (smem > 200 * 1024) B2_FAIL(-4, "topk_merge: too many lists x k for one warp's shared memory");
     if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topk_merge_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, smem, ctx->stream>>>(
-        keys, L, nq, k, list_stride, out_dist_f, out_dist_i, out_id, out_key);
+        keys, nullptr, L, nq, k, list_stride, out_dist_f, out_dist_i, out_id, out_key);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_topk_merge_ptrs(Ctx* ctx, const unsigned long long* const* list_ptrs_dev, int L, long long nq, int k, float* out_dist_f,
+                           int* out_dist_i, unsigned long long* out_id, unsigned long long* out_key) {
+    if (nq <= 0) return 0;
+    int warps = 4;
+    while (warps > 1 && (size_t)warps * L * k * 8 > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * L * k * 8;
+    if (smem > 200 * 1024) B2_FAIL(-4, "topk_merge: too many lists x k for one warp's shared memory");
+    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_merge_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, smem, ctx->stream>>>(nullptr, list_ptrs_dev, L, nq, k, 0,
+                                                                                               out_dist_f, out_dist_i, out_id, out_key);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;

@@ -107,6 +107,45 @@ def train_pq_model(x_rot: np.ndarray, M: int, ksub: int = 256, K: int = 1, iters
     return coarse, cb
 
 
+def _kmeans_fast(x: np.ndarray, k: int, iters: int, rng: np.random.Generator) -> np.ndarray:
+    """Lloyd k-means with a vectorised update (sort by assignment + segmented sums in double): the SURVEY.md 8(d)
+    protocol (25 iterations, 256 centroids per sub-space, 100 k rows) in seconds.  Used for the BENCH models; the test
+    models keep _kmeans (their golden files pin its output)."""
+    n, d = x.shape
+    c = x[rng.choice(n, size=k, replace=n < k)].copy()
+    for _ in range(iters):
+        g = x @ (np.float32(-2.0) * c).T          # |x|^2 is constant per row: argmin of |c|^2 - 2<x,c>
+        g += (c * c).sum(1)[None, :]
+        a = g.argmin(1)
+        cnt = np.bincount(a, minlength=k)
+        nz = cnt > 0
+        order = np.argsort(a, kind="stable")
+        starts = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+        sums = np.add.reduceat(x[order].astype(np.float64), starts[nz], axis=0)
+        c[nz] = (sums / cnt[nz, None]).astype(np.float32)
+        if (~nz).any():
+            c[~nz] = x[rng.integers(n, size=int((~nz).sum()))]
+    return c.astype(np.float32)
+
+
+def train_pq_model_bench(x_rot: np.ndarray, M: int, ksub: int = 256, iters: int = 25, seed: int = SEED_KMEANS):
+    """Flat-ADC (K = 1, zero coarse centroid) codebooks for the benchmark workloads: seeded Lloyd, `iters` iterations over
+    all rows given (the first 100 k rows of the database, already in the permuted space).  Sub-spaces are
+    independent (own generator, seed + m) and trained on a thread pool."""
+    import concurrent.futures as cf
+    import os
+    x = np.ascontiguousarray(x_rot, dtype=np.float32)
+    D = x.shape[1]
+    ds = D // M
+
+    def one(m):
+        return _kmeans_fast(np.ascontiguousarray(x[:, m * ds:(m + 1) * ds]), ksub, iters, np.random.Generator(np.random.PCG64(seed + 7919 * m)))
+    threads = max(1, min(M, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+    with cf.ThreadPoolExecutor(max_workers=threads) as ex:
+        cb = np.stack(list(ex.map(one, range(M)))).astype(np.float32)
+    return np.zeros((1, D), dtype=np.float32), cb
+
+
 def write_opq_model(path: str, coarse: np.ndarray, cb: np.ndarray, reorder: np.ndarray) -> None:
     """int32 D,K,M,ksub | f32 coarse[K][D] | f32 cb[M][ksub][D/M] | int32 reorder[D]."""
     K, D = coarse.shape

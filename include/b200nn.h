@@ -38,6 +38,8 @@ typedef struct b200nn_flat* b200nn_flat_t;
 typedef struct b200nn_pq* b200nn_pq_t;
 typedef struct b200nn_sq* b200nn_sq_t;
 typedef struct b200nn_proj* b200nn_proj_t;
+typedef struct b200nn_comm* b200nn_comm_t; /* one rank of a multi-GPU job (NCCL communicator + exchange buffers) */
+typedef struct b200nn_mpq* b200nn_mpq_t;   /* (O)PQ index row-sharded over several GPUs of one process */
 
 /* ---- context ---------------------------------------------------------------------------- */
 const char* b200nn_last_error(void);
@@ -78,6 +80,11 @@ int b200nn_flat_search_dev(b200nn_flat_t idx, const void* queries_dev, size_t nq
                            uint64_t* out_label_dev);
 int b200nn_flat_save(b200nn_flat_t idx, const char* path);  /* byte format of brutoforce.hpp:95-106 */
 int b200nn_flat_load(b200nn_ctx_t ctx, int metric, int order, size_t dim, const char* path, b200nn_flat_t* out);
+/* the vectors and labels of a hnswlib::HierarchicalNSW<dist_t>::saveIndex file (hnsw_sifts_retrieval/hnswlib/hnswalg.h:491-519;
+ * what makeSearch.cpp:19-22 opens) as a flat exact index: the graph is not used, searchKnn becomes exact. */
+int b200nn_flat_load_hnsw(b200nn_ctx_t ctx, int metric, int order, size_t dim, const char* path, b200nn_flat_t* out);
+/* capacity, row count and (optionally) the labels in row order */
+int b200nn_flat_info(b200nn_flat_t idx, size_t* max_elements, size_t* n, uint64_t* labels_out, size_t labels_capacity);
 
 /* ---- (O)PQ / IVFOPQ ----------------------------------------------------------------------
  * Model = D, K coarse centroids, M sub-quantizers x ksub(=256) codewords, and the "rotation":
@@ -107,6 +114,12 @@ int b200nn_pq_build_lut(b200nn_pq_t idx, const float* q_rotated, size_t nq, int 
                         float* out_lut);
 /* IVFOPQ::QueryThrehold: out_scores [nq, n_groups], clamp-initialised, min-aggregated per group. */
 int b200nn_pq_scores(b200nn_pq_t idx, const float* q_raw, size_t nq, int nprobe, float* out_scores);
+/* device variant: rows of out_scores_dev are out_stride >= n_groups floats apart (a shard of a larger index writes into
+ * the matrix of ALL groups; columns it holds no rows of keep the clamp value). */
+int b200nn_pq_scores_dev(b200nn_pq_t idx, const float* q_raw_dev, size_t nq, int nprobe, size_t out_stride, float* out_scores_dev);
+/* append n rows that are already coded (host pointers; what an index file holds): coarse list id, videoId
+ * (NULL: id = row) and M code bytes per row.  Ids and code bytes are validated. */
+int b200nn_pq_append_coded(b200nn_pq_t idx, const int32_t* lists, const int32_t* group_ids, const uint8_t* codes, size_t n);
 /* What the reference's query main does with Query's output (opq/src/multi_frame_index_test.cpp:54-68): query
  * video v = frames [frame_off[v], frame_off[v+1]) of q_raw; per frame the QueryThrehold scores (above), summed
  * over the video's frames per indexed videoId in frame order (fp32, from 0.0f), then get_sort_results
@@ -134,8 +147,51 @@ int b200nn_topk_merge_grid_dev(b200nn_ctx_t ctx, const uint64_t* keys_dev, int n
  * (two {query group, output slice, granule lo, granule hi} segments; granule = 64 rows), slices = lists per query. */
 int b200nn_pq_scan_plan(int sm_count, int M, size_t nq, size_t n_rows, int* n_full, int* n_tail, int* slices, int32_t* desc,
                         size_t desc_capacity);
-int b200nn_pq_save_index(b200nn_pq_t idx, const char* dir_or_path, const char* const* group_paths); /* App. A-3 */
+int b200nn_pq_save_index(b200nn_pq_t idx, const char* dir_or_path, const char* const* group_paths); /* App. A-3; group_paths holds n_groups entries */
+/* the same with the length of group_paths stated: groups past n_paths get an empty name (IVFOPQ::Add called directly
+ * leaves m_imgNum behind the highest videoId, so the shim's path table can be shorter than the group count) */
+int b200nn_pq_save_index_n(b200nn_pq_t idx, const char* dir_or_path, const char* const* group_paths, size_t n_paths);
 int b200nn_pq_load_index(b200nn_ctx_t ctx, const char* path, const int32_t* perm, float clamp, b200nn_pq_t* out);
+/* ---- several GPUs (the coded database shards by rows, queries are replicated, ONE exchange of the
+ * per-shard top-k records, a per-query merge).  Global ids order ties exactly as a single index does.
+ *
+ * (1) one process per GPU (torchrun, MPI, ...): rank 0 draws an id, every rank builds a communicator on its context's
+ *     device (ncclCommInitRank; NCCL is bound at run time, libnccl.so.2) and calls pq_search_sharded_dev collectively. */
+#define B200NN_COMM_ID_BYTES 128
+int b200nn_comm_get_unique_id(void* id128);
+int b200nn_comm_create(b200nn_ctx_t ctx, int rank, int nranks, const void* id128, b200nn_comm_t* out);
+void b200nn_comm_destroy(b200nn_comm_t comm);
+int b200nn_comm_info(b200nn_comm_t comm, int* rank, int* nranks, int* nccl_version);
+/* Ranks form a (query chunk x row shard) grid, rank = chunk * row_shards + shard; row_shards = nranks is the plain
+ * row-sharded layout.  q_raw_dev = the WHOLE batch [nq, D] on this rank's device, id_base = global id of the shard's
+ * first row.  Local scan of this rank's query chunk -> one ncclAllGather of [chunk_q, k] records -> merge: out_*_dev
+ * receive the full [nq, k] result on every rank.  Enqueued on the context stream, not synchronised. */
+int b200nn_pq_search_sharded_dev(b200nn_pq_t shard, b200nn_comm_t comm, int row_shards, const float* q_raw_dev, size_t nq, int nprobe,
+                                 size_t k, uint64_t id_base, float* out_dist_dev, uint64_t* out_id_dev);
+/* host-only: the (row shards x query chunks) grid for n_ranks GPUs from a measured cost model; row_shards = n_ranks (plain
+ * row sharding) unless a 1/n_ranks shard is too small to amortise the per-query top-k warm-up of the scan. */
+int b200nn_plan_layout(int n_ranks, uint64_t n_rows, uint64_t batch, int M, int k, int sm_count, int* row_shards, int* query_chunks);
+/* (2) one process, several GPUs: the IVFOPQ drop-in over devices[] (replaces the same IVFOPQ methods as b200nn_pq_*;
+ *     the C++ shim picks it when $B200NN_DEVICES lists more than one device).  Every add call's rows are dealt to the
+ *     shards in contiguous blocks.  Exchange: devices with peer access (NVLink) merge straight out of each other's
+ *     memory -- device g merges query chunk g, the gather is inside the merge kernel; otherwise, or with
+ *     $B200NN_EXCHANGE=nccl, one ncclAllGather (ncclCommInitAll).  Host buffers in and out. */
+int b200nn_mpq_create(const int* devices, int n_devices, int D, int K, int M, int ksub, const float* coarse, const float* codebooks,
+                      const int32_t* perm, const float* R, float clamp_threshold, b200nn_mpq_t* out);
+int b200nn_mpq_load_model(const int* devices, int n_devices, const char* model_path, b200nn_mpq_t* out);
+void b200nn_mpq_destroy(b200nn_mpq_t idx);
+int b200nn_mpq_info(b200nn_mpq_t idx, int* D, int* K, int* M, int* ksub, uint64_t* n_rows, uint64_t* n_groups, int* n_devices,
+                    int* peer_exchange);
+int b200nn_mpq_shard_rows(b200nn_mpq_t idx, uint64_t* rows /*[n_devices]*/);
+int b200nn_mpq_set_clamp(b200nn_mpq_t idx, float clamp_threshold);
+int b200nn_mpq_rotate(b200nn_mpq_t idx, const float* x, size_t n, float* y);
+int b200nn_mpq_add(b200nn_mpq_t idx, const float* x_raw, size_t n, const int32_t* group_ids);
+int b200nn_mpq_add_rotated(b200nn_mpq_t idx, const float* x_rotated, size_t n, const int32_t* group_ids);
+int b200nn_mpq_search(b200nn_mpq_t idx, const float* q_raw, size_t nq, int nprobe, size_t k, float* out_dist, uint64_t* out_id);
+int b200nn_mpq_scores(b200nn_mpq_t idx, const float* q_raw, size_t nq, int nprobe, float* out_scores); /* elementwise min over shards */
+int b200nn_mpq_save_index(b200nn_mpq_t idx, const char* dir_or_path, const char* const* group_paths, size_t n_paths);
+int b200nn_mpq_load_index(const int* devices, int n_devices, const char* path, const int32_t* perm, float clamp, b200nn_mpq_t* out);
+
 /* timing of the last pq_search[_dev] stages in ms: [rotate, lut, scan, merge] (CUDA events). */
 int b200nn_pq_last_timing(b200nn_pq_t idx, float* ms4);
 /* bytes of device memory held by the coded database (codes as scanned). */

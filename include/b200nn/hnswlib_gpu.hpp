@@ -19,6 +19,8 @@
 #include <stdint.h>
 
 #include <cstdlib>
+#include <cstring>
+#include <fstream>
 #include <queue>
 #include <stdexcept>
 #include <string>
@@ -42,6 +44,20 @@ inline b200nn_ctx_t default_ctx() {
 }
 inline void check(int rc) {
     if (rc != 0) throw std::runtime_error(b200nn_last_error());
+}
+// $B200NN_DEVICES = "0,1,2,3": the GPUs a sharded index spreads over (empty / one entry: the single default context)
+inline std::vector<int> env_devices() {
+    std::vector<int> d;
+    const char* e = std::getenv("B200NN_DEVICES");
+    if (!e) return d;
+    for (const char* p = e; *p;) {
+        char* end = nullptr;
+        const long v = std::strtol(p, &end, 10);
+        if (end == p) break;
+        d.push_back((int)v);
+        p = (*end == ',') ? end + 1 : end;
+    }
+    return d;
 }
 // how a space tells the GPU index what to compute
 struct GpuMetric {
@@ -162,7 +178,10 @@ public:
         count_++;
         if (pend_labels_.size() >= 8192) flush();
     }
+    // Deviation, on purpose: for a label that was never added the reference's `dict_external_to_internal[cur_external]`
+    // (brutoforce.hpp:59) default-inserts internal id 0 and so silently deletes the FIRST stored row; here it is an error.
     void removePoint(labeltype cur_external) {
+        if (!labels_.count((uint64_t)cur_external)) throw std::runtime_error("removePoint: label not found");
         flush();
         b200nn::check(b200nn_flat_remove(h_, (uint64_t)cur_external));
         labels_.erase((uint64_t)cur_external);
@@ -189,13 +208,26 @@ public:
         flush();
         b200nn::check(b200nn_flat_save(h_, location.c_str()));
     }
-    void loadIndex(const std::string& location, SpaceInterface<dist_t>* s) {
+    void loadIndex(const std::string& location, SpaceInterface<dist_t>* s) { load_file(location, s, false); }
+
+protected:
+    // hnsw_format: the file is a HierarchicalNSW::saveIndex file (hnswalg.h:491-519) whose vectors + labels are taken
+    void load_file(const std::string& location, SpaceInterface<dist_t>* s, bool hnsw_format) {
         bind(s);
         if (h_) b200nn_flat_destroy(h_);
         h_ = nullptr;
-        b200nn::check(b200nn_flat_load(b200nn::default_ctx(), metric_, order_, dim_, location.c_str(), &h_));
-        b200nn::check(b200nn_flat_size(h_, &count_));
-        // labels of a loaded index are known to the library; duplicates are then caught at flush time
+        pend_rows_.clear();
+        pend_labels_.clear();
+        labels_.clear();
+        b200nn::check(hnsw_format ? b200nn_flat_load_hnsw(b200nn::default_ctx(), metric_, order_, dim_, location.c_str(), &h_)
+                                  : b200nn_flat_load(b200nn::default_ctx(), metric_, order_, dim_, location.c_str(), &h_));
+        // the reference restores maxelements_ from the file (brutoforce.hpp:113) and keeps its label map implicit in data_;
+        // here capacity and labels come back from the library so that addPoint after a load sees the same limit and the
+        // same "Ids have to be unique" check as before the save
+        b200nn::check(b200nn_flat_info(h_, &maxelements_, &count_, nullptr, 0));
+        std::vector<uint64_t> labs(count_);
+        b200nn::check(b200nn_flat_info(h_, nullptr, nullptr, labs.data(), labs.size()));
+        labels_.insert(labs.begin(), labs.end());
     }
 };
 
@@ -208,8 +240,24 @@ class ExactNSW : public BruteforceSearch<dist_t> {
 public:
     ExactNSW(SpaceInterface<dist_t>* s, size_t max_elements, size_t /*M*/ = 16, size_t /*ef_construction*/ = 200)
         : BruteforceSearch<dist_t>(s, max_elements) {}
-    ExactNSW(SpaceInterface<dist_t>* s, const std::string& location) : BruteforceSearch<dist_t>(s, location) {}
+    // HierarchicalNSW(space, location, nmslib = false) (hnswalg.h:31-34): `location` is the HNSW index file the
+    // reference's makeIdx wrote (or a file saved by this class, which is BruteforceSearch's format) -- told apart by the
+    // header: a HierarchicalNSW file starts with offsetLevel0_ == 0, a brute-force file with maxelements_ > 0
+    ExactNSW(SpaceInterface<dist_t>* s, const std::string& location, bool /*nmslib*/ = false) : BruteforceSearch<dist_t>(s) {
+        std::ifstream in(location.c_str(), std::ios::binary);
+        size_t first = 1;
+        in.read((char*)&first, sizeof first);
+        if (!in) throw std::runtime_error("Cannot open index file " + location);
+        this->load_file(location, s, first == 0);
+    }
     void setEf(size_t) {}  // exact search: nothing to tune
 };
+
+#ifdef B200NN_HNSW_DROP_IN
+// For sources that name the class directly (hnsw_sifts_retrieval/siftsIndex.hpp:49 `hnswlib::HierarchicalNSW<float>* appr_alg`,
+// makeIdx.cpp:321-325): with -DB200NN_HNSW_DROP_IN they compile UNMODIFIED and get the exact GPU scan.
+template <typename dist_t>
+using HierarchicalNSW = ExactNSW<dist_t>;
+#endif
 
 }  // namespace hnswlib

@@ -54,10 +54,12 @@ inline std::vector<std::pair<float, unsigned> > get_sort_results(const std::vect
 
 class IVFOPQ {
 public:
-    IVFOPQ() : m_imgLocation(NULL), m_maxIndexNum(1 << 30) {}
-    explicit IVFOPQ(int maxIndexNum) : m_imgLocation(NULL), m_maxIndexNum(maxIndexNum) {}
+    // $B200NN_DEVICES="0,1,..." with more than one entry: the index is row-sharded over those GPUs (b200nn_mpq_*),
+    // same answers as on one GPU; otherwise the single default context (b200nn_pq_*).
+    IVFOPQ() : m_imgLocation(NULL), m_maxIndexNum(1 << 30), devices_(b200nn::env_devices()) {}
+    explicit IVFOPQ(int maxIndexNum) : m_imgLocation(NULL), m_maxIndexNum(maxIndexNum), devices_(b200nn::env_devices()) {}
     ~IVFOPQ() {
-        b200nn_pq_destroy(h_);
+        drop();
         delete[] m_imgLocation;
     }
     IVFOPQ(const IVFOPQ&) = delete;
@@ -78,9 +80,10 @@ public:
         perm_.resize(D_);
         fin.read((char*)perm_.data(), 4LL * D_);
         if (!fin) { printf("Can not open the model file!\n"); return 0; }
-        if (h_) b200nn_pq_destroy(h_);
-        h_ = NULL;
-        if (b200nn_pq_load_model(b200nn::default_ctx(), modelFile.c_str(), &h_) != 0) {
+        drop();
+        const int rc = multi() ? b200nn_mpq_load_model(devices_.data(), (int)devices_.size(), modelFile.c_str(), &mh_)
+                               : b200nn_pq_load_model(b200nn::default_ctx(), modelFile.c_str(), &h_);
+        if (rc != 0) {
             printf("%s\n", b200nn_last_error());
             return 0;
         }
@@ -94,14 +97,17 @@ public:
         std::vector<float> raw;
         if (!read_raw(srcFile, raw, m_frameNum)) return;
         Init2DArray(m_ppFeat, m_frameNum, D_);
-        if (m_frameNum > 0) b200nn::check(b200nn_pq_rotate(h_, raw.data(), (size_t)m_frameNum, m_ppFeat[0]));
+        if (m_frameNum > 0)
+            b200nn::check(multi() ? b200nn_mpq_rotate(mh_, raw.data(), (size_t)m_frameNum, m_ppFeat[0])
+                                  : b200nn_pq_rotate(h_, raw.data(), (size_t)m_frameNum, m_ppFeat[0]));
     }
 
     // IVFOPQ.cpp:105-174: rows are already reordered; every row gets the current videoId (m_imgNum)
     void Add(float** m_ppFeat, const int m_frameNum) {
         if (m_frameNum <= 0) return;
         std::vector<int32_t> gid(m_frameNum, (int32_t)m_imgNum_);
-        b200nn::check(b200nn_pq_add_rotated(h_, m_ppFeat[0], (size_t)m_frameNum, gid.data()));
+        b200nn::check(multi() ? b200nn_mpq_add_rotated(mh_, m_ppFeat[0], (size_t)m_frameNum, gid.data())
+                              : b200nn_pq_add_rotated(h_, m_ppFeat[0], (size_t)m_frameNum, gid.data()));
     }
 
     // IVFOPQ.cpp:176-211
@@ -131,10 +137,20 @@ public:
         int n = 0;
         if (!read_raw(featFile, raw, n) || n == 0) return;
         uint64_t ng = 0;
-        b200nn::check(b200nn_pq_info(h_, NULL, NULL, NULL, NULL, NULL, &ng));
+        b200nn::check(multi() ? b200nn_mpq_info(mh_, NULL, NULL, NULL, NULL, NULL, &ng, NULL, NULL)
+                              : b200nn_pq_info(h_, NULL, NULL, NULL, NULL, NULL, &ng));
+        const uint64_t ng_lib = ng;
         ng = std::max<uint64_t>(ng, (uint64_t)m_imgNum_);
         std::vector<float> flat((size_t)n * ng, 1.0f);
-        if (ng) b200nn::check(b200nn_pq_scores(h_, raw.data(), (size_t)n, nk, flat.data()));
+        if (ng_lib == ng) {
+            if (ng) b200nn::check(multi() ? b200nn_mpq_scores(mh_, raw.data(), (size_t)n, nk, flat.data())
+                                          : b200nn_pq_scores(h_, raw.data(), (size_t)n, nk, flat.data()));
+        } else if (ng_lib) {  // the path table is longer than the highest videoId stored: the extra columns keep the clamp value
+            std::vector<float> part((size_t)n * ng_lib);
+            b200nn::check(multi() ? b200nn_mpq_scores(mh_, raw.data(), (size_t)n, nk, part.data())
+                                  : b200nn_pq_scores(h_, raw.data(), (size_t)n, nk, part.data()));
+            for (int f = 0; f < n; f++) std::copy(part.begin() + (size_t)f * ng_lib, part.begin() + (size_t)(f + 1) * ng_lib, flat.begin() + (size_t)f * ng);
+        }
         matchScore.resize(n);
         for (int f = 0; f < n; f++) matchScore[f].assign(flat.begin() + (size_t)f * ng, flat.begin() + (size_t)(f + 1) * ng);
     }
@@ -144,7 +160,10 @@ public:
         std::cout << "save index file..." << std::endl;
         std::vector<const char*> paths(m_imgNum_);
         for (int i = 0; i < m_imgNum_; i++) paths[i] = m_imgLocation[i].ptr;
-        b200nn::check(b200nn_pq_save_index(h_, desDir.c_str(), paths.data()));
+        // Add() called directly tags rows with videoId = m_imgNum without advancing it (IVFOPQ.cpp:132), so the index may
+        // hold one group more than there are paths: the library is told how many entries the table has
+        b200nn::check(multi() ? b200nn_mpq_save_index(mh_, desDir.c_str(), paths.data(), paths.size())
+                              : b200nn_pq_save_index_n(h_, desDir.c_str(), paths.data(), paths.size()));
     }
 
     // reads SaveIndex's output (see header note); LoadModel must have been called (for the reorder table)
@@ -157,10 +176,17 @@ public:
         }
         int hdr[5];
         fin.read((char*)hdr, sizeof hdr);
-        b200nn_pq_t nh = NULL;
-        b200nn::check(b200nn_pq_load_index(b200nn::default_ctx(), srcFile.c_str(), perm_.empty() ? NULL : perm_.data(), 1.0f, &nh));
-        if (h_) b200nn_pq_destroy(h_);
-        h_ = nh;
+        if (multi()) {
+            b200nn_mpq_t nh = NULL;
+            b200nn::check(b200nn_mpq_load_index(devices_.data(), (int)devices_.size(), srcFile.c_str(), perm_.empty() ? NULL : perm_.data(), 1.0f, &nh));
+            drop();
+            mh_ = nh;
+        } else {
+            b200nn_pq_t nh = NULL;
+            b200nn::check(b200nn_pq_load_index(b200nn::default_ctx(), srcFile.c_str(), perm_.empty() ? NULL : perm_.data(), 1.0f, &nh));
+            drop();
+            h_ = nh;
+        }
         D_ = hdr[0]; K_ = hdr[1]; M_ = hdr[2]; ksub_ = hdr[3];
         m_imgNum_ = hdr[4];
         // trailing path table: imgNum x char[260]
@@ -176,6 +202,7 @@ public:
 
     // extensions
     b200nn_pq_t handle() const { return h_; }
+    b200nn_mpq_t multi_handle() const { return mh_; }
     int imgNum() const { return m_imgNum_; }
 
 private:
@@ -194,7 +221,16 @@ private:
         fin.read((char*)raw.data(), 4LL * n * D_);
         return true;
     }
+    bool multi() const { return devices_.size() > 1; }
+    void drop() {
+        if (h_) b200nn_pq_destroy(h_);
+        if (mh_) b200nn_mpq_destroy(mh_);
+        h_ = NULL;
+        mh_ = NULL;
+    }
     b200nn_pq_t h_ = NULL;
+    b200nn_mpq_t mh_ = NULL;
+    std::vector<int> devices_;
     int D_ = 0, K_ = 0, M_ = 0, ksub_ = 0, m_imgNum_ = 0, m_maxIndexNum;
     std::vector<int32_t> perm_;
 };
