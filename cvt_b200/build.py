@@ -80,6 +80,12 @@ def build_tools(force: bool = False, verbose: bool = False):
         if force or _newer([s, LIB] + hdrs, o):
             _run([gxx, "-O2", "-std=c++14", "-I", os.path.join(ROOT, "include"), s, "-o", o, "-L", LIBDIR, "-lb200nn",
                   "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../../cvt_b200/lib"], o + ".log")
+    # standalone CUDA measurement programs (tools/*.cu), e.g. the bare int8 MMA peak
+    for s_ in sorted(glob.glob(os.path.join(tdir, "*.cu"))):
+        o = os.path.join(bdir, os.path.basename(s_)[:-3])
+        outs.append(o)
+        if force or _newer([s_], o):
+            _run([NVCC] + ARCH + ["-O3", "-lineinfo", "-o", o, s_], o + ".log")
     # the reference's OWN mains, unmodified, compiled in place against the forwarding headers and linked with
     # libb200nn: the drop-in proof (only where /root/reference exists; the binaries then travel with the snapshot).
     # A quoted #include resolves next to the including file FIRST, so compiling the reference file by path would
@@ -108,6 +114,39 @@ def build_tools(force: bool = False, verbose: bool = False):
                 raise RuntimeError(f"{name} does not import {need}: it was not compiled against the drop-in headers")
         if os.path.exists(o):
             outs.append(o)
+    # hnsw_sifts_retrieval/makeSearch.cpp + siftsIndex.cpp (the other caller north_star names) on the drop-in headers:
+    # -DB200NN_HNSW_DROP_IN makes hnswlib::HierarchicalNSW<float> (siftsIndex.hpp:49, siftsIndex.cpp:6) the exact GPU index
+    # that reads the HNSW index file.  OpenCV is absent from this image: tests/stubs/opencv2 stands in for it (float matrices;
+    # the "SIFT detector" reads descriptors the real cv2 SIFT produced).  The only edit of the sources: the hard-coded
+    # /Users/willard/... path prefixes become the relative data/ (sed) -- the same edit oracle/Makefile makes for the CPU build.
+    ref_dir = "/root/reference/hnsw_sifts_retrieval"
+    o = os.path.join(bdir, "ref_makeSearch_on_b200nn")
+    srcs = [os.path.join(ref_dir, "makeSearch.cpp"), os.path.join(ref_dir, "siftsIndex.cpp"), os.path.join(ref_dir, "siftsIndex.hpp")]
+    stubs = os.path.join(ROOT, "tests", "stubs")
+    if all(os.path.exists(s) for s in srcs) and (force or _newer(srcs + [LIB] + hdrs + glob.glob(os.path.join(stubs, "opencv2", "*.hpp")), o)):
+        txt = open(srcs[0], "rb").read()
+        for pre in (b"/Users/willard/codes/cpp/hnsw_sift_retrieval/hnsw_sifts_retrieval/data/", b"/Users/willard/projects/bovw/data/"):
+            txt = txt.replace(pre, b"data/")
+        common = [gxx, "-O2", "-std=c++11", "-DB200NN_HNSW_DROP_IN", "-I", compat, "-I", ref_dir, "-I", stubs]
+        o1, o2 = os.path.join(OBJDIR, "makeSearch_dropin.o"), os.path.join(OBJDIR, "siftsIndex_dropin.o")
+        r = subprocess.run(common + ["-x", "c++", "-", "-c", "-o", o1], input=txt, cwd=OBJDIR, capture_output=True)
+        log = r.stdout + r.stderr
+        if r.returncode == 0:
+            r = subprocess.run(common + ["-c", srcs[1], "-o", o2], cwd=OBJDIR, capture_output=True)
+            log += r.stdout + r.stderr
+        if r.returncode == 0:
+            r = subprocess.run([gxx, o1, o2, "-o", o, "-L", LIBDIR, "-lb200nn", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath,$ORIGIN/../../cvt_b200/lib"],
+                               capture_output=True)
+            log += r.stdout + r.stderr
+        open(o + ".log", "wb").write(log)
+        if r.returncode != 0:
+            sys.stderr.write(log.decode(errors="replace"))
+            raise RuntimeError("build failed: ref_makeSearch_on_b200nn")
+        if b"b200nn_flat_load_hnsw" not in open(o, "rb").read():
+            os.remove(o)
+            raise RuntimeError("ref_makeSearch_on_b200nn was not compiled against the drop-in headers")
+    if os.path.exists(o):
+        outs.append(o)
     return outs
 
 

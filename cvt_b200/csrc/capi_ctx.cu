@@ -5,6 +5,27 @@
 namespace b200nn {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+int ensure_copy_engine(Ctx* c, size_t bytes) {
+    if (!c->copy_stream) {
+        B2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            B2_CUDA(cudaEventCreateWithFlags(&c->copy_done[b], cudaEventDisableTiming));
+            B2_CUDA(cudaEventCreateWithFlags(&c->compute_done[b], cudaEventDisableTiming));
+        }
+    }
+    if (bytes > c->pinned_bytes) {
+        B2_CUDA(cudaStreamSynchronize(c->copy_stream));
+        for (int b = 0; b < 2; b++) {
+            if (c->pinned[b]) cudaFreeHost(c->pinned[b]);
+            c->pinned[b] = nullptr;
+        }
+        c->pinned_bytes = 0;
+        for (int b = 0; b < 2; b++) B2_CUDA(cudaMallocHost(&c->pinned[b], bytes));
+        c->pinned_bytes = bytes;
+    }
+    return 0;
+}
 }  // namespace b200nn
 
 using namespace b200nn;
@@ -48,6 +69,12 @@ void b200nn_ctx_destroy(b200nn_ctx_t ctx) {
         if (ctx->c.events[i]) cudaEventDestroy(ctx->c.events[i]);
     if (ctx->c.d_err) cudaFree(ctx->c.d_err);
     if (ctx->c.dmat) cudaFree(ctx->c.dmat);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->c.pinned[b]) cudaFreeHost(ctx->c.pinned[b]);
+        if (ctx->c.copy_done[b]) cudaEventDestroy(ctx->c.copy_done[b]);
+        if (ctx->c.compute_done[b]) cudaEventDestroy(ctx->c.compute_done[b]);
+    }
+    if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.own_stream);
     delete ctx;
 }

@@ -32,7 +32,7 @@ struct b200nn_flat {
     DevBuf<int> xnorm;   // per-tile row meta: |x|^2 and label rank
     DevBuf<int> ws_thr;  // [nq][k] distances of the sample pass (column k-1 = the bound the full pass starts from)
     DevBuf<unsigned char> ws_q;
-    DevBuf<unsigned long long> ws_keys, ws_id;
+    DevBuf<unsigned long long> ws_keys, ws_id, ws_best;  // ws_best: the best k of the passes so far (sorted keys)
     DevBuf<float> ws_dist;
 };
 
@@ -101,29 +101,53 @@ int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, vo
             p->tc_rows = (long long)p->n;
         }
         const int groups = u8_scan_tc_lists_per_slice((int)p->dim, (int)k);
-        const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, (long long)p->n), L = S * groups;
-        if ((rc = p->ws_keys.ensure((size_t)L * nq * k))) return rc;
-        // Every (slice, group) list pays its own top-k warm-up of ~k ln(rows/k) insertions.  For a large index a first
-        // pass over a 16 k-row prefix yields each query's exact k-th best distance there -- an upper bound on its global
-        // k-th best -- and the full pass starts from that bound instead of +inf (exact: ties at the bound are kept).
-        const long long n_sample = 16384;
-        const int* init_thr = nullptr;
-        if ((long long)p->n >= 16 * n_sample && !getenv("B200NN_NO_U8_SAMPLE")) {
-            const int Sa = u8_scan_tc_slices(c->sm_count, (long long)nq, n_sample);
-            if (Sa * groups > L) B2_FAIL(B200NN_ERR_STATE, "flat_search: sample pass needs more lists than the full pass");
-            if ((rc = p->ws_thr.ensure(nq * k))) return rc;
-            if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, n_sample, (int)p->dim, (const unsigned char*)q_dev, (long long)nq, Sa,
-                                        (int)k, nullptr, 0, p->ws_keys.p)))
-                return rc;
-            if ((rc = launch_topk_merge(c, p->ws_keys.p, Sa * groups, (long long)nq, (int)k, (long long)(nq * k), nullptr, p->ws_thr.p, nullptr,
-                                        nullptr)))
-                return rc;
-            init_thr = p->ws_thr.p + (k - 1);
+        const long long tiles = ((long long)p->n + 255) / 256;
+        // Every (slice, group) list pays its own top-k warm-up, and a chunk of accumulators that holds a survivor costs the
+        // epilogue twice what a clean one does.  A large index is therefore scanned in passes of growing size -- 64 tiles
+        // (16 k rows), 8 x as many, then the rest -- and each pass starts from the exact k-th best distance of everything
+        // before it (an upper bound on the final k-th best; ties are kept, so the result is exact): by the last pass, which
+        // holds 7/8 of the rows, the bound sits at a selectivity of k / 131072.
+        long long bounds[4] = {0, tiles, tiles, tiles};
+        int n_pass = 1;
+        if (tiles >= 16 * 64 && !getenv("B200NN_NO_U8_SAMPLE")) {
+            bounds[1] = 64; bounds[2] = 512; bounds[3] = tiles;
+            n_pass = 3;
         }
-        if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, (long long)p->n, (int)p->dim, (const unsigned char*)q_dev, (long long)nq, S,
-                                    (int)k, init_thr, (int)k, p->ws_keys.p)))
+        int Lmax = 0;
+        for (int ps = 0; ps < n_pass; ps++)
+            Lmax = std::max(Lmax, u8_scan_tc_slices(c->sm_count, (long long)nq, bounds[ps + 1] - bounds[ps]) * groups + 1);
+        if ((rc = p->ws_keys.ensure((size_t)Lmax * nq * k))) return rc;
+        if (n_pass > 1 && ((rc = p->ws_thr.ensure(nq * k)) || (rc = p->ws_best.ensure(nq * k)))) return rc;
+        for (int ps = 0; ps < n_pass; ps++) {
+            const long long t0 = bounds[ps], nt = bounds[ps + 1] - bounds[ps];
+            const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, nt);
+            int L = S * groups;
+            if (nt <= 0) B2_CUDA(cudaMemsetAsync(p->ws_keys.p, 0xFF, (size_t)L * nq * k * sizeof(unsigned long long), c->stream));  // empty index
+            if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, (long long)p->n, t0, nt, (int)p->dim, (const unsigned char*)q_dev, (long long)nq, S,
+                                        (int)k, ps ? p->ws_thr.p + (k - 1) : nullptr, (int)k, p->ws_keys.p)))
+                return rc;
+            if (ps) {  // the best k of the earlier passes ride along as one more list
+                B2_CUDA(cudaMemcpyAsync(p->ws_keys.p + (size_t)L * nq * k, p->ws_best.p, nq * k * sizeof(unsigned long long), cudaMemcpyDeviceToDevice,
+                                        c->stream));
+                L++;
+            }
+            const bool last = ps == n_pass - 1;
+            if ((rc = launch_topk_merge(c, p->ws_keys.p, L, (long long)nq, (int)k, (long long)(nq * k), nullptr, last ? (int*)out_dist : p->ws_thr.p,
+                                        last ? out_label : nullptr, last ? nullptr : p->ws_best.p)))
+                return rc;
+        }
+        return launch_rank_to_label(c, out_label, (long long)(nq * k), p->label_sorted.p);
+    }
+    if (p->metric != 2) {  // fp32: register-tiled all-pairs distances in the reference's accumulation order + selection
+        long long cr;
+        int nc, S;
+        flat_f32_plan(c->sm_count, (long long)nq, (long long)p->n, &cr, &nc, &S);
+        const int L = nc * S;
+        if ((rc = p->ws_keys.ensure((size_t)L * nq * k))) return rc;
+        if ((rc = launch_flat_scan_f32(c, p->metric, p->order, (const float*)p->data.p, p->rank.p, (long long)p->n, (int)p->dim, (const float*)q_dev,
+                                       (long long)nq, (int)k, p->ws_keys.p)))
             return rc;
-        if ((rc = launch_topk_merge(c, p->ws_keys.p, L, (long long)nq, (int)k, (long long)(nq * k), nullptr, (int*)out_dist, out_label, nullptr)))
+        if ((rc = launch_topk_merge(c, p->ws_keys.p, L, (long long)nq, (int)k, (long long)(nq * k), (float*)out_dist, nullptr, out_label, nullptr)))
             return rc;
         return launch_rank_to_label(c, out_label, (long long)(nq * k), p->label_sorted.p);
     }
@@ -132,8 +156,7 @@ int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, vo
     if ((rc = launch_flat_scan(c, p->metric, p->order, p->data.p, p->rank.p, (long long)p->n, (int)p->dim, q_dev, (long long)nq, S,
                                (int)k, p->ws_keys.p)))
         return rc;
-    if ((rc = launch_topk_merge(c, p->ws_keys.p, S, (long long)nq, (int)k, (long long)(nq * k), p->metric == 2 ? nullptr : (float*)out_dist,
-                                p->metric == 2 ? (int*)out_dist : nullptr, out_label, nullptr)))
+    if ((rc = launch_topk_merge(c, p->ws_keys.p, S, (long long)nq, (int)k, (long long)(nq * k), nullptr, (int*)out_dist, out_label, nullptr)))
         return rc;
     return launch_rank_to_label(c, out_label, (long long)(nq * k), p->label_sorted.p);
 }

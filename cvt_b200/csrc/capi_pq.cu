@@ -547,26 +547,46 @@ int b200nn_pq_add_rotated(b200nn_pq_t p, const float* x_rotated, size_t n, const
     return pq_add_host(p, x_rotated, n, group_ids, true);
 }
 
+// IVFOPQ::Add from host memory.  The rows go through two pinned staging buffers (kept by the context) and two device
+// buffers: while the kernels of one block (rotate, coarse assign, encode) run on the context stream, the next block is
+// copied into its pinned buffer by the host and sent ahead on a second stream -- the copies hide behind the encode instead
+// of queueing in front of it (pageable, single-buffered, synchronous before: 0.75 s per 10^6 rows at K = 8192, 0.15 s of
+// it kernels).
 static int pq_add_host(b200nn_pq_t p, const float* x_raw, size_t n, const int32_t* group_ids, bool already_rotated) {
     if (!p || (n && !x_raw)) B2_FAIL(B200NN_ERR_INVALID, "pq_add: NULL argument");
     if (!n) return 0;
     Guard g(p);
     Ctx* c = &p->ctx->c;
-    // stage through a bounded device buffer so that huge host arrays do not need a device twin
-    const size_t chunk = 1 << 20;
-    DevBuf<float> stage;
-    DevBuf<int> gstage;
+    const size_t blk = std::max<size_t>(1024, std::min<size_t>(n, (size_t)(32u << 20) / (sizeof(float) * p->D)));  // <= 32 MB per block
     int rc;
-    if ((rc = stage.ensure(std::min(chunk, n) * p->D))) return rc;
-    if (group_ids && (rc = gstage.ensure(std::min(chunk, n)))) return rc;
-    for (size_t off = 0; off < n; off += chunk) {
-        const size_t cn = std::min(chunk, n - off);
-        B2_CUDA(cudaMemcpyAsync(stage.p, x_raw + off * p->D, sizeof(float) * cn * p->D, cudaMemcpyHostToDevice, c->stream));
-        if (group_ids) B2_CUDA(cudaMemcpyAsync(gstage.p, group_ids + off, sizeof(int) * cn, cudaMemcpyHostToDevice, c->stream));
-        if ((rc = add_dev_locked(p, stage.p, (long long)cn, group_ids ? gstage.p : nullptr, group_ids ? group_ids + off : nullptr,
+    if ((rc = ensure_copy_engine(c, blk * p->D * sizeof(float)))) return rc;
+    DevBuf<float> stage[2];
+    DevBuf<int> gstage[2];
+    for (int b = 0; b < 2; b++) {
+        if ((rc = stage[b].ensure(blk * p->D))) return rc;
+        if (group_ids && (rc = gstage[b].ensure(blk))) return rc;
+    }
+    // grow the row store once, not per block
+    if ((rc = p->codes.reserve((size_t)(p->n + n) * p->M, (size_t)p->n * p->M, c->stream)) ||
+        (rc = p->list.reserve((size_t)(p->n + n), (size_t)p->n, c->stream)) || (rc = p->group.reserve((size_t)(p->n + n), (size_t)p->n, c->stream)))
+        return rc;
+    int b = 0;
+    for (size_t off = 0; off < n; off += blk, b ^= 1) {
+        const size_t cn = std::min(blk, n - off);
+        // pinned[b] / stage[b] were last used by block (off - 2 blk): its copy and its kernels must be done
+        B2_CUDA(cudaEventSynchronize(c->copy_done[b]));
+        B2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->compute_done[b], 0));
+        memcpy(c->pinned[b], x_raw + off * p->D, cn * p->D * sizeof(float));
+        B2_CUDA(cudaMemcpyAsync(stage[b].p, c->pinned[b], cn * p->D * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+        if (group_ids) B2_CUDA(cudaMemcpyAsync(gstage[b].p, group_ids + off, sizeof(int) * cn, cudaMemcpyHostToDevice, c->copy_stream));
+        B2_CUDA(cudaEventRecord(c->copy_done[b], c->copy_stream));
+        B2_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done[b], 0));
+        if ((rc = add_dev_locked(p, stage[b].p, (long long)cn, group_ids ? gstage[b].p : nullptr, group_ids ? group_ids + off : nullptr,
                                  already_rotated)))
             return rc;
+        B2_CUDA(cudaEventRecord(c->compute_done[b], c->stream));
     }
+    B2_CUDA(cudaStreamSynchronize(c->copy_stream));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }

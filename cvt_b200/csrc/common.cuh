@@ -38,7 +38,13 @@ struct Ctx {
     int* d_err = nullptr;  // device-side error flag (smem layout overflow etc.)
     float* dmat = nullptr;  // row-chunk distance matrix of the tiled nearest-centroid path (dist_tile.cu), grown on demand
     size_t dmat_elems = 0;
+    // host -> device staging for the add paths: a copy stream, two pinned buffers and their events (created on first use)
+    cudaStream_t copy_stream = nullptr;
+    void* pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes = 0;
+    cudaEvent_t copy_done[2] = {}, compute_done[2] = {};
 };
+int ensure_copy_engine(Ctx* ctx, size_t bytes_per_buffer);  // capi_ctx.cu
 
 // ------------------------------------------------------------------------------------ keys
 // 64-bit sortable record: (orderable(dist) << 32) | id.  Comparing records as unsigned integers

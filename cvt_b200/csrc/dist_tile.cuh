@@ -13,4 +13,12 @@ bool tiled_nearest_pays(int d, int K);
 int launch_tiled_nearest(Ctx* ctx, const float* x, long long ld, int col0, long long n, int d, const float* cT, int K, int rule, int nk,
                          int* out_idx, float* out_dist);
 
+// a3 on the register tile (ksub = 256, D/M in {4, 8, 16}): codes[r*M + m] = first minimum over the 256 codewords of sub-quantizer m
+// of the sequential fp32 squared distance to the residual x - coarse[list[r]]; cbT = codebooks transposed to [M][D/M][256]
+bool pq_encode_tile_supported(int ds, int ksub);
+int launch_pq_encode_tile(Ctx* ctx, const float* x, long long n, int D, const float* coarse, const int* list, const float* cbT, int M, int ksub,
+                          unsigned char* codes);
+// the context's distance scratch matrix (at least `elems` floats)
+int ensure_dmat(Ctx* ctx, size_t elems);
+
 }  // namespace b200nn

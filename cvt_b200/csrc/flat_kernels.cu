@@ -7,10 +7,10 @@
 // 4 = SSE, 8 = AVX), lane l sums elements l, l+L, ... (mul then add, never fused), lanes added left
 // to right -- so distances are bit-identical and the (dist, label) order matches the max-heap rule.
 //
-// One CTA = QT queries x a slice of rows.  A lane owns a row, keeps QT*L accumulators in
-// registers and streams its row with 16-byte loads; queries are broadcast from shared memory.
-// Selection: ballot-compacted staging + sorted CTA lists (topk.cuh); keys carry the RANK of the
-// row's label so that ties resolve on the label exactly as std::pair<dist_t,labeltype> does.
+// The fp32 metrics run on the register-tiled kernel of flat_tile.cu; this file keeps the generic uint8 kernel (metric 2
+// for shapes the tensor-core kernel of u8_scan_tc.cu does not take): one CTA = QT queries x a slice of rows, a lane owns
+// a row, queries are broadcast from shared memory.  Selection: ballot-compacted staging + sorted CTA lists (topk.cuh);
+// keys carry the RANK of the row's label so that ties resolve on the label exactly as std::pair<dist_t,labeltype> does.
 #include <algorithm>
 
 #include "flat_kernels.cuh"
@@ -28,112 +28,6 @@ struct FlatShared {
     unsigned long long tau[FLAT_QT];
     int lock[FLAT_QT];
 };
-
-template <int METRIC, int L>
-__global__ void __launch_bounds__(FLAT_WARPS * 32)
-flat_scan_f32_kernel(const float* __restrict__ data, const uint32_t* __restrict__ rank, long long n, int d,
-                     const float* __restrict__ queries, long long nq, int n_slices, int k,
-                     unsigned long long* __restrict__ out_keys /*[slice][nq][k]*/) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FlatShared& S = *reinterpret_cast<FlatShared*>(smem_raw);
-    float* s_q = reinterpret_cast<float*>(smem_raw + sizeof(FlatShared));  // [QT][d]
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long q0 = (long long)blockIdx.x * FLAT_QT;
-    const int slice = blockIdx.y;
-    for (int i = threadIdx.x; i < FLAT_QT * KP; i += blockDim.x) (&S.list[0][0])[i] = KEY_MAX;
-    if (threadIdx.x < FLAT_QT) { S.tau[threadIdx.x] = KEY_MAX; S.lock[threadIdx.x] = 0; }
-    for (int i = threadIdx.x; i < FLAT_QT * d; i += blockDim.x) {
-        const int qq = i / d;
-        s_q[i] = (q0 + qq < nq) ? queries[(q0 + qq) * d + (i - qq * d)] : 0.0f;
-    }
-    __syncthreads();
-    const long long r_lo = (n * slice) / n_slices, r_hi = (n * (slice + 1)) / n_slices;
-    int cnt[FLAT_QT];
-#pragma unroll
-    for (int t = 0; t < FLAT_QT; t++) cnt[t] = 0;
-    volatile unsigned long long* tau = S.tau;
-
-    for (long long base = r_lo + (long long)w * 32; base < r_hi; base += FLAT_WARPS * 32) {
-        const long long row = base + lane;
-        const bool valid = row < r_hi;
-        float acc[FLAT_QT][L];
-#pragma unroll
-        for (int t = 0; t < FLAT_QT; t++)
-#pragma unroll
-            for (int l = 0; l < L; l++) acc[t][l] = 0.0f;
-        if (valid) {
-            const float* x = data + row * d;
-            if ((d & 3) == 0) {
-                for (int i = 0; i < d; i += 4) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(x + i));
-                    const float xv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        // (i + e) % L with i % 4 == 0: compile-time for L in {1,4}; for L == 8 depends on i & 4
-#pragma unroll
-                        for (int t = 0; t < FLAT_QT; t++) {
-                            const float qv = s_q[t * d + i + e];
-                            float term;
-                            if (METRIC == 0) term = __fmul_rn(qv, xv[e]);
-                            else { const float df = __fsub_rn(qv, xv[e]); term = __fmul_rn(df, df); }
-                            if (L == 1) acc[t][0] = __fadd_rn(acc[t][0], term);
-                            else if (L == 4) acc[t][e] = __fadd_rn(acc[t][e], term);
-                            else {
-                                if (i & 4) acc[t][(4 + e) % L] = __fadd_rn(acc[t][(4 + e) % L], term);
-                                else acc[t][e % L] = __fadd_rn(acc[t][e % L], term);
-                            }
-                        }
-                    }
-                }
-            } else {  // scalar loop (only L == 1 reaches here: d % 4 != 0 selects InnerProduct/L2Sqr)
-                for (int i = 0; i < d; i++) {
-                    const float xe = __ldg(x + i);
-#pragma unroll
-                    for (int t = 0; t < FLAT_QT; t++) {
-                        const float qv = s_q[t * d + i];
-                        float term;
-                        if (METRIC == 0) term = __fmul_rn(qv, xe);
-                        else { const float df = __fsub_rn(qv, xe); term = __fmul_rn(df, df); }
-                        acc[t][0] = __fadd_rn(acc[t][0], term);
-                    }
-                }
-            }
-        }
-        const uint32_t rk = valid ? rank[row] : 0u;
-#pragma unroll
-        for (int t = 0; t < FLAT_QT; t++) {
-            float sum = acc[t][0];
-#pragma unroll
-            for (int l = 1; l < L; l++) sum = __fadd_rn(sum, acc[t][l]);
-            const float dist = (METRIC == 0) ? __fsub_rn(1.0f, sum) : sum;
-            const unsigned long long key = make_key(f32_orderable(dist), rk);
-            const bool pass = valid && (q0 + t < nq) && key < tau[t];
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                const uint32_t st = smem_u32(&S.stage[w][t][0]);
-                if (pass) sts64(st + (uint32_t)(cnt[t] + __popc(m & ((1u << lane) - 1))) * 8u, key);
-                cnt[t] += __popc(m);
-                __syncwarp();
-                if (cnt[t] > FLAT_SBW - 32) {
-                    for (int off = 0; off < cnt[t]; off += 32)
-                        warp_flush(smem_u32(&S.list[t][0]), &S.lock[t], tau + t, st + off * 8, min(32, cnt[t] - off), k);
-                    cnt[t] = 0;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < FLAT_QT; t++) {
-        const uint32_t st = smem_u32(&S.stage[w][t][0]);
-        for (int off = 0; off < cnt[t]; off += 32)
-            warp_flush(smem_u32(&S.list[t][0]), &S.lock[t], tau + t, st + off * 8, min(32, cnt[t] - off), k);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < FLAT_QT * k; i += blockDim.x) {
-        const int t = i / k, j = i - t * k;
-        if (q0 + t < nq) out_keys[((long long)slice * nq + q0 + t) * k + j] = S.list[t][j];
-    }
-}
 
 // L2SqrI: res += (a-b)*(a-b) over the first (d>>2)*4 bytes (space_l2.h:199-213), exact int32.
 // |a-b| fits a byte, so 4 squared differences = one __vabsdiffu4 + one dp4a.
@@ -236,45 +130,20 @@ int flat_pick_slices(int sm_count, long long nq, long long n) {
     return (int)s;
 }
 
-template <int METRIC, int L>
-static int flat_f32_dispatch(Ctx* ctx, const float* data, const uint32_t* rank, long long n, int d, const float* q,
-                             long long nq, int S, int k, unsigned long long* out_keys) {
-    const size_t smem = sizeof(FlatShared) + (size_t)FLAT_QT * d * sizeof(float);
-    B2_CUDA(cudaFuncSetAttribute(flat_scan_f32_kernel<METRIC, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((nq + FLAT_QT - 1) / FLAT_QT), (unsigned)S);
-    flat_scan_f32_kernel<METRIC, L><<<grid, FLAT_WARPS * 32, smem, ctx->stream>>>(data, rank, n, d, q, nq, S, k, out_keys);
-    ctx->launches++;
-    B2_CUDA(cudaGetLastError());
-    return 0;
-}
-
 int launch_flat_scan(Ctx* ctx, int metric, int order, const void* data, const uint32_t* rank, long long n, int d,
                      const void* queries, long long nq, int n_slices, int k, unsigned long long* out_keys) {
     if (nq <= 0) return 0;
     if (k < 1 || k > KP) B2_FAIL(-4, "flat search supports 1 <= k <= 128");
     if ((size_t)d * FLAT_QT * 4 + sizeof(FlatShared) > 200 * 1024) B2_FAIL(-4, "flat search: dimension too large");
-    const float* fd = (const float*)data;
-    const float* fq = (const float*)queries;
-    if (metric == 2) {
-        const size_t smem = sizeof(FlatShared) + (size_t)FLAT_QT * (d >> 2) * 4 + 16;
-        B2_CUDA(cudaFuncSetAttribute(flat_scan_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)((nq + FLAT_QT - 1) / FLAT_QT), (unsigned)n_slices);
-        flat_scan_u8_kernel<<<grid, FLAT_WARPS * 32, smem, ctx->stream>>>((const unsigned char*)data, rank, n, d,
-                                                                        (const unsigned char*)queries, nq, n_slices, k, out_keys);
-        ctx->launches++;
-        B2_CUDA(cudaGetLastError());
-        return 0;
-    }
-    if (metric == 0) {
-        if (order == 1) return flat_f32_dispatch<0, 1>(ctx, fd, rank, n, d, fq, nq, n_slices, k, out_keys);
-        if (order == 4) return flat_f32_dispatch<0, 4>(ctx, fd, rank, n, d, fq, nq, n_slices, k, out_keys);
-        if (order == 8) return flat_f32_dispatch<0, 8>(ctx, fd, rank, n, d, fq, nq, n_slices, k, out_keys);
-    } else if (metric == 1) {
-        if (order == 1) return flat_f32_dispatch<1, 1>(ctx, fd, rank, n, d, fq, nq, n_slices, k, out_keys);
-        if (order == 4) return flat_f32_dispatch<1, 4>(ctx, fd, rank, n, d, fq, nq, n_slices, k, out_keys);
-        if (order == 8) return flat_f32_dispatch<1, 8>(ctx, fd, rank, n, d, fq, nq, n_slices, k, out_keys);
-    }
-    B2_FAIL(-1, "flat search: bad metric/order");
+    if (metric != 2) B2_FAIL(-1, "launch_flat_scan: the fp32 metrics run on the tiled kernel (launch_flat_scan_f32, flat_tile.cu)");
+    const size_t smem = sizeof(FlatShared) + (size_t)FLAT_QT * (d >> 2) * 4 + 16;
+    B2_CUDA(cudaFuncSetAttribute(flat_scan_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((nq + FLAT_QT - 1) / FLAT_QT), (unsigned)n_slices);
+    flat_scan_u8_kernel<<<grid, FLAT_WARPS * 32, smem, ctx->stream>>>((const unsigned char*)data, rank, n, d,
+                                                                    (const unsigned char*)queries, nq, n_slices, k, out_keys);
+    ctx->launches++;
+    B2_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int launch_rank_to_label(Ctx* ctx, unsigned long long* ids, long long count, const unsigned long long* label_sorted) {

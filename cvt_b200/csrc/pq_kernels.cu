@@ -880,16 +880,20 @@ __global__ void frame_sum_kernel(const float* scores, int n_frames, long long ng
     }
 }
 
-// k smallest (value, index) records of each row of a dense [rows][n] fp32 matrix; one CTA per row.
+// k smallest (value, id) records of each row of a dense fp32 matrix (row stride ld); CTA (row, slice) scans its share of the
+// n columns.  id = id_map[column] when a map is given (the flat index passes the RANK of every row's label, so that ties
+// resolve on the label as std::pair<dist_t, labeltype> does), else the column index.  out_keys [slice][rows][k].
 __global__ void __launch_bounds__(256)
-dense_topk_kernel(const float* __restrict__ values, long long n, int k, unsigned long long* __restrict__ out_keys) {
+dense_topk_kernel(const float* __restrict__ values, long long n, long long ld, int k, const uint32_t* __restrict__ id_map,
+                  unsigned long long* __restrict__ out_keys) {
     constexpr int SBW = 64;
     __shared__ __align__(16) unsigned long long s_list[KP];
     __shared__ __align__(16) unsigned long long s_stage[8][SBW];
     __shared__ unsigned long long s_tau;
     __shared__ int s_lock;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const float* v = values + (long long)blockIdx.x * n;
+    const float* v = values + (long long)blockIdx.x * ld;
+    const long long c_lo = (n * blockIdx.y) / gridDim.y, c_hi = (n * (blockIdx.y + 1)) / gridDim.y;
     for (int i = threadIdx.x; i < KP; i += blockDim.x) s_list[i] = KEY_MAX;
     if (threadIdx.x == 0) { s_tau = KEY_MAX; s_lock = 0; }
     __syncthreads();
@@ -900,10 +904,10 @@ dense_topk_kernel(const float* __restrict__ values, long long n, int k, unsigned
         for (int off = 0; off < cnt; off += 32) warp_flush(L, &s_lock, tau_p, ST + off * 8, min(32, cnt - off), k);
         cnt = 0;
     };
-    for (long long r0 = (long long)w * 32; r0 < n; r0 += 8 * 32) {
+    for (long long r0 = c_lo + (long long)w * 32; r0 < c_hi; r0 += 8 * 32) {
         const long long r = r0 + lane;
         unsigned long long key = KEY_MAX;
-        if (r < n) key = make_key(f32_orderable(v[r]), (uint32_t)r);
+        if (r < c_hi) key = make_key(f32_orderable(v[r]), id_map ? __ldg(id_map + r) : (uint32_t)r);
         const bool pass = key < *tau_p;
         const unsigned msk = __ballot_sync(0xffffffffu, pass);
         if (msk) {
@@ -915,7 +919,8 @@ dense_topk_kernel(const float* __restrict__ values, long long n, int k, unsigned
     }
     flush_all();
     __syncthreads();
-    for (int j = threadIdx.x; j < k; j += blockDim.x) out_keys[(long long)blockIdx.x * k + j] = s_list[j];
+    unsigned long long* out = out_keys + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * k;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) out[j] = s_list[j];
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
@@ -956,6 +961,8 @@ int launch_pq_encode(Ctx* ctx, const float* x, long long n, int D, const float* 
                      int M, int ksub, unsigned char* codes) {
     if (n == 0) return 0;
     const int ds = D / M;
+    if (pq_encode_tile_supported(ds, ksub) && n >= 64 && !getenv("B200NN_NO_ENCODE_TILE"))  // the register-tiled kernel (dist_tile.cu)
+        return launch_pq_encode_tile(ctx, x, n, D, coarse, list, cbT, M, ksub, codes);
     const unsigned grid = grid_for(n * M, 8, ctx->sm_count, 16);
 #define B2_ENC(DS_)                                                                                              \
     case DS_:                                                                                                    \
@@ -1168,14 +1175,19 @@ int launch_frame_sum(Ctx* ctx, const float* scores, int n_frames, long long ng, 
     return 0;
 }
 
-int launch_dense_topk(Ctx* ctx, const float* values, long long rows, long long n, int k, unsigned long long* out_keys) {
+int launch_dense_topk_ex(Ctx* ctx, const float* values, long long rows, long long n, long long ld, int k, int slices, const uint32_t* id_map,
+                         unsigned long long* out_keys) {
     if (rows <= 0) return 0;
     if (k < 1 || k > KP) B2_FAIL(-4, "dense top-k supports 1 <= k <= 128");
     if (n > 0xFFFFFFFFLL) B2_FAIL(-4, "dense top-k: more than 2^32 columns");
-    dense_topk_kernel<<<(unsigned)rows, 256, 0, ctx->stream>>>(values, n, k, out_keys);
+    dense_topk_kernel<<<dim3((unsigned)rows, (unsigned)std::max(1, slices)), 256, 0, ctx->stream>>>(values, n, ld, k, id_map, out_keys);
     ctx->launches++;
     B2_CUDA(cudaGetLastError());
     return 0;
+}
+
+int launch_dense_topk(Ctx* ctx, const float* values, long long rows, long long n, int k, unsigned long long* out_keys) {
+    return launch_dense_topk_ex(ctx, values, rows, n, n, k, 1, nullptr, out_keys);
 }
 
 int launch_fill_f32(Ctx* ctx, float* p, long long n, float v) {

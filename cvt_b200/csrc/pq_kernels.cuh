@@ -33,6 +33,9 @@ int launch_fill_f32(Ctx* ctx, float* p, long long n, float v);
 // f-5: total[g] = sequential fp32 sum over frames of scores[f][g]; k smallest (value, index) per row of a dense matrix
 int launch_frame_sum(Ctx* ctx, const float* scores, int n_frames, long long ng, float* total);
 int launch_dense_topk(Ctx* ctx, const float* values, long long rows, long long n, int k, unsigned long long* out_keys);
+// row stride ld, `slices` column slices per row (out_keys [slices][rows][k]), ids = id_map[column] when given
+int launch_dense_topk_ex(Ctx* ctx, const float* values, long long rows, long long n, long long ld, int k, int slices, const uint32_t* id_map,
+                         unsigned long long* out_keys);
 int launch_ivf_scan(Ctx* ctx, const float* lut, const int* probes, const long long* list_off, const unsigned char* codes_sorted,
                     const int* slot_sorted, int M, int ksub, long long nq, int nprobe, long long out_stride, float* out);
 int launch_ivf_search_topk(Ctx* ctx, const float* q_rot, long long nq, int D, const int* probes, int nprobe, const float* coarse,

@@ -42,7 +42,7 @@ __global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, c
         if (key == KEY_MAX) continue;
         real++;
         int rank = j;
-        for (int l2 = 0; l2 < L; l2++) {
+        for (int l2 = 0; l2 < L && rank < k; l2++) {  // a key already ranked past k is out whatever the other lists hold
             if (l2 == l) continue;
             const unsigned long long* o = sk + l2 * k;
             int lo = 0, hi = k;
@@ -64,6 +64,69 @@ __global__ void topk_merge_kernel(const unsigned long long* __restrict__ keys, c
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) real += __shfl_xor_sync(0xffffffffu, real, s);
     for (int r = real + lane; r < k; r += 32) {
+        const long long o = q * k + r;
+        if (out_dist_f) out_dist_f[o] = __int_as_float(0x7f800000);
+        if (out_dist_i) out_dist_i[o] = 0x7fffffff;
+        if (out_id) out_id[o] = 0xFFFFFFFFFFFFFFFFull;
+        if (out_key) out_key[o] = KEY_MAX;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Few queries, many lists (a small batch cut into up to one piece per SM: L ~ 19 at 64 queries x 20 k rows): one warp per
+// query leaves most of the machine idle while that warp walks L*k*(L-1) binary searches.  Here a whole CTA works on one
+// query: same rank rule, the keys are spread over all threads.  Same layout and outputs as topk_merge_kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void topk_merge_cta_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* const* __restrict__ ptrs, int L,
+                                      long long nq, int k, long long list_stride, float* __restrict__ out_dist_f, int* __restrict__ out_dist_i,
+                                      unsigned long long* __restrict__ out_id, unsigned long long* __restrict__ out_key) {
+    extern __shared__ unsigned long long sk[];  // [L*k]
+    __shared__ int s_real;
+    const long long q = blockIdx.x;
+    if (threadIdx.x == 0) s_real = 0;
+    if (ptrs) {
+        for (int e = threadIdx.x; e < L * k; e += blockDim.x) {
+            const int l = e / k, j = e - l * k;
+            sk[e] = ptrs[l][q * k + j];
+        }
+    } else {
+        const long long cq = list_stride / k, chunk = q / cq;
+        const unsigned long long* base = keys + (chunk * (L - 1) * cq + q) * k;
+        for (int e = threadIdx.x; e < L * k; e += blockDim.x) {
+            const int l = e / k, j = e - l * k;
+            sk[e] = base[(long long)l * list_stride + j];
+        }
+    }
+    __syncthreads();
+    int real = 0;
+    for (int e = threadIdx.x; e < L * k; e += blockDim.x) {
+        const int l = e / k, j = e - l * k;
+        const unsigned long long key = sk[e];
+        if (key == KEY_MAX) continue;
+        real++;
+        int rank = j;
+        for (int l2 = 0; l2 < L && rank < k; l2++) {  // a key already ranked past k is out whatever the other lists hold
+            if (l2 == l) continue;
+            const unsigned long long* o = sk + l2 * k;
+            int lo = 0, hi = k;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (o[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            const long long o = q * k + rank;
+            const uint32_t ord = (uint32_t)(key >> 32);
+            if (out_dist_f) out_dist_f[o] = f32_from_orderable(ord);
+            if (out_dist_i) out_dist_i[o] = s32_from_orderable(ord);
+            if (out_id) out_id[o] = key & 0xFFFFFFFFull;
+            if (out_key) out_key[o] = key;
+        }
+    }
+    if (real) atomicAdd(&s_real, real);
+    __syncthreads();
+    for (int r = s_real + threadIdx.x; r < k; r += blockDim.x) {
         const long long o = q * k + r;
         if (out_dist_f) out_dist_f[o] = __int_as_float(0x7f800000);
         if (out_dist_i) out_dist_i[o] = 0x7fffffff;
@@ -129,6 +192,14 @@ int launch_topk_merge(Ctx* ctx, const unsigned long long* keys, int L, long long
         const int wq = 4;
         topk_merge_extract_kernel<<<(unsigned)((nq + wq - 1) / wq), wq * 32, 0, ctx->stream>>>(keys, L, nq, k, list_stride, out_dist_f,
                                                                                              out_dist_i, out_id, out_key);
+        ctx->launches++;
+        B2_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (L >= 3 && nq <= 4LL * ctx->sm_count && (size_t)L * k * 8 <= 200 * 1024) {  // small batch: a CTA per query
+        const size_t smem = (size_t)L * k * 8;
+        if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(topk_merge_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        topk_merge_cta_kernel<<<(unsigned)nq, 256, smem, ctx->stream>>>(keys, nullptr, L, nq, k, list_stride, out_dist_f, out_dist_i, out_id, out_key);
         ctx->launches++;
         B2_CUDA(cudaGetLastError());
         return 0;

@@ -20,7 +20,12 @@
 //   label ranks ride along as a second 2 KB copy, so the epilogue never touches global memory.
 //   The epilogue keeps two tcgen05.ld of 32 columns in flight per warp (register double buffer) and
 //   filters a chunk with one running minimum per query; the exact mask is built only for chunks that hit.
-// Supported: D % 32 == 0, D <= 256, k <= 32 (otherwise the dp4a kernel of flat_kernels.cu is used).
+// A launch covers a RANGE of tiles: the caller (capi_flat.cu) scans a large index in passes of growing size -- a 16 k-row
+// prefix, then 8x as many rows, then the rest -- and hands each pass the exact k-th best distance of everything scanned
+// before it as the starting threshold (an upper bound on the final k-th best: exact, ties kept), so that by the time the bulk
+// of the rows streams by, a 32 x 32 chunk of accumulators rarely holds a survivor at all.
+// Supported: D % 32 == 0, D <= 256, k <= 120 as far as the lists fit shared memory beside the operand tiles (k <= 120 at
+// D = 128 with one epilogue group); otherwise the dp4a kernel of flat_kernels.cu is used.
 #include <stdint.h>
 
 #include <algorithm>
@@ -32,7 +37,7 @@ namespace b200nn {
 
 constexpr int TC_M = 128;      // queries per CTA (TMEM lanes)
 constexpr int TC_N = 256;      // database rows per tile
-constexpr int TC_KP = 32;      // list slots per query (k <= 32)
+constexpr int TC_KP = 120;     // most list slots per query (what fits shared memory at D = 128, one epilogue group)
 constexpr int TC_MAX_SMEM = 232448;  // 227 KB
 constexpr int TC_META_BYTES = 2 * TC_N * 4;  // per tile: 256 x |x|^2 then 256 x label rank
 
@@ -56,16 +61,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// THREAD-private top-k list of k <= 32 keys in shared memory, kept UNSORTED with its maximum tracked in registers
+// THREAD-private top-k list of k keys in shared memory, kept UNSORTED with its maximum tracked in registers
 // (tkey at slot tpos; KEY_MAX while a slot is still empty): an insertion overwrites the maximum and rescans the k
 // slots for the new one -- k independent loads instead of a dependent shift chain.  Sorted once at the end.
+// Layout: slot-major, slot j of query t at L_addr + (j * 128) * 8 with L_addr already offset by t: the threads of a warp
+// walk the same slot of 32 different lists together, which is conflict-free for any k.
+constexpr uint32_t TC_SLOT_STRIDE = 128u * 8u;
 __device__ __forceinline__ void list_replace_max(uint32_t L_addr, unsigned long long key, int k, unsigned long long& tkey, int& tpos) {
-    sts64(L_addr + (uint32_t)tpos * 8u, key);
+    sts64(L_addr + (uint32_t)tpos * TC_SLOT_STRIDE, key);
     unsigned long long mx = 0;
     int mp = 0;
 #pragma unroll 4
     for (int j = 0; j < k; j++) {
-        const unsigned long long v = lds64(L_addr + (uint32_t)j * 8u);
+        const unsigned long long v = lds64(L_addr + (uint32_t)j * TC_SLOT_STRIDE);
         if (v >= mx) { mx = v; mp = j; }
     }
     tkey = mx;
@@ -76,7 +84,8 @@ template <int TC_GROUPS>
 __global__ void __launch_bounds__(TC_GROUPS * 128 + 32, 1)
 u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32][8][16] canonical B tiles
                   const int* __restrict__ xmeta,             // [tiles][2][256]: |x|^2 (padded rows: large), label rank
-                  long long n, int D, const unsigned char* __restrict__ queries, long long nq, int n_slices, int k,
+                  long long n, long long tile0, long long n_tiles,  // rows indexed; this launch scans tiles [tile0, tile0 + n_tiles)
+                  int D, const unsigned char* __restrict__ queries, long long nq, int n_slices, int k,
                   const int* __restrict__ init_thr, int init_stride,  // optional: an upper bound on each query's k-th best distance
                   int NS,                                              // B-tile ring stages (2..4, as many as shared memory allows)
                   unsigned long long* __restrict__ out_keys /*[slice * groups + group][nq][k]*/) {
@@ -99,8 +108,7 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long q0 = (long long)blockIdx.x * TC_M;
     const int slice = blockIdx.y;
-    const long long n_tiles = (n + TC_N - 1) / TC_N;
-    const long long t_lo = (n_tiles * slice) / n_slices, t_hi = (n_tiles * (slice + 1)) / n_slices;
+    const long long t_lo = tile0 + (n_tiles * slice) / n_slices, t_hi = tile0 + (n_tiles * (slice + 1)) / n_slices;
     const int T = (int)(t_hi - t_lo);
     const uint32_t A_LBO = (TC_M / 8) * 128, B_LBO = (TC_N / 8) * 128, SBO = 128;
     const int ksteps = D / 32;
@@ -182,7 +190,7 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
         // ===== epilogue group g = warp / 4: thread owns query ql = tid % 128 (TMEM lane ql), columns [128 g, 128 g + 128) of every tile =====
         const int grp = warp >> 2, ql = tid & (TC_M - 1);
         const bool qvalid = q0 + ql < nq;
-        const uint32_t myList = sList + (uint32_t)((grp * TC_M + ql) * k) * 8u;
+        const uint32_t myList = sList + (uint32_t)(grp * TC_M * k + ql) * 8u;  // slot j at + j * TC_SLOT_STRIDE
         const uint32_t scratch = sScratch + (uint32_t)warp * (32 * 32 * 4) + (uint32_t)lane * 4u;
         int qn;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(qn) : "r"(sQn + (uint32_t)ql * 4u));
@@ -271,10 +279,10 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
         if (qvalid) {  // emit the list ascending: rank of an entry = how many entries order before it
             unsigned long long* out = out_keys + ((long long)(slice * TC_GROUPS + grp) * nq + q0 + ql) * k;
             for (int j = 0; j < k; j++) {
-                const unsigned long long e = lds64(myList + (uint32_t)j * 8u);
+                const unsigned long long e = lds64(myList + (uint32_t)j * TC_SLOT_STRIDE);
                 int rank = 0;
                 for (int i = 0; i < k; i++) {
-                    const unsigned long long o = lds64(myList + (uint32_t)i * 8u);
+                    const unsigned long long o = lds64(myList + (uint32_t)i * TC_SLOT_STRIDE);
                     rank += (o < e || (o == e && i < j)) ? 1 : 0;  // empty slots (KEY_MAX) tie: index order
                 }
                 out[rank] = e;
@@ -340,17 +348,18 @@ int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint3
     return 0;
 }
 
-int u8_scan_tc_slices(int sm_count, long long nq, long long n) {
-    const long long qt = (nq + TC_M - 1) / TC_M, tiles = (n + TC_N - 1) / TC_N;
+int u8_scan_tc_slices(int sm_count, long long nq, long long n_tiles) {
+    const long long qt = (nq + TC_M - 1) / TC_M, tiles = n_tiles;
     long long s = sm_count / qt;  // one wave of one-CTA-per-SM
     s = std::max<long long>(1, std::min<long long>(s, std::max<long long>(1, tiles / 4)));
     return (int)std::min<long long>(s, 1024);
 }
 
-int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, int D, const unsigned char* queries,
-                      long long nq, int n_slices, int k, const int* init_thr, int init_stride, unsigned long long* out_keys) {
-    if (nq <= 0) return 0;
-    if (!u8_scan_tc_supported(D, k)) B2_FAIL(-4, "u8 tensor-core scan: needs D % 32 == 0, D <= 256, k <= 32");
+int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, long long tile0, long long n_tiles, int D,
+                      const unsigned char* queries, long long nq, int n_slices, int k, const int* init_thr, int init_stride,
+                      unsigned long long* out_keys) {
+    if (nq <= 0 || n_tiles <= 0) return 0;
+    if (!u8_scan_tc_supported(D, k)) B2_FAIL(-4, "u8 tensor-core scan: needs D % 32 == 0, D <= 256 and k lists that fit shared memory");
     const int groups = u8_scan_tc_lists_per_slice(D, k);
     int stages = 4;  // B-tile ring: as deep as shared memory allows (hides the TMA latency behind two epilogues and more)
     while (stages > 2 && tc_smem_bytes(D, k, groups, stages) > (size_t)TC_MAX_SMEM) stages--;
@@ -358,10 +367,10 @@ int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, lon
     dim3 grid((unsigned)((nq + TC_M - 1) / TC_M), (unsigned)n_slices);
     if (groups == 2) {
         B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        u8_scan_tc_kernel<2><<<grid, 2 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, init_thr, init_stride, stages, out_keys);
+        u8_scan_tc_kernel<2><<<grid, 2 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, tile0, n_tiles, D, queries, nq, n_slices, k, init_thr, init_stride, stages, out_keys);
     } else {
         B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        u8_scan_tc_kernel<1><<<grid, 1 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, D, queries, nq, n_slices, k, init_thr, init_stride, stages, out_keys);
+        u8_scan_tc_kernel<1><<<grid, 1 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, tile0, n_tiles, D, queries, nq, n_slices, k, init_thr, init_stride, stages, out_keys);
     }
     ctx->launches++;
     B2_CUDA(cudaGetLastError());

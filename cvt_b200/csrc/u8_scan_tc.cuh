@@ -9,12 +9,14 @@ bool u8_scan_tc_supported(int D, int k);
 // (n_pad = multiple of 256; xmeta holds 2 * n_pad ints)
 int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint32_t* rank, long long n, int D, unsigned char* xcan,
                                 int* xmeta, long long n_pad);
-int u8_scan_tc_slices(int sm_count, long long nq, long long n);
+int u8_scan_tc_slices(int sm_count, long long nq, long long n_tiles);  // row slices for a pass over n_tiles tiles of 256 rows
 int u8_scan_tc_lists_per_slice(int D, int k);
 // out_keys [n_slices * u8_scan_tc_lists_per_slice(D, k)][nq][k]; ids in the keys are label ranks.
 // init_thr (may be NULL): init_thr[q * init_stride] = an upper bound on query q's k-th best distance, e.g. the k-th
 // best over a prefix of the rows -- rows beyond it are dropped (ties kept), so lists may come back shorter than k.
-int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, int D, const unsigned char* queries,
-                      long long nq, int n_slices, int k, const int* init_thr, int init_stride, unsigned long long* out_keys);
+// The launch scans tiles [tile0, tile0 + n_tiles) of the index (n = rows indexed, for the validity of the last tile).
+int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, long long tile0, long long n_tiles, int D,
+                      const unsigned char* queries, long long nq, int n_slices, int k, const int* init_thr, int init_stride,
+                      unsigned long long* out_keys);
 
 }  // namespace b200nn
