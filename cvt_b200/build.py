@@ -118,7 +118,7 @@ def build_tools(force: bool = False, verbose: bool = False):
     # -DB200NN_HNSW_DROP_IN makes hnswlib::HierarchicalNSW<float> (siftsIndex.hpp:49, siftsIndex.cpp:6) the exact GPU index
     # that reads the HNSW index file.  OpenCV is absent from this image: tests/stubs/opencv2 stands in for it (float matrices;
     # the "SIFT detector" reads descriptors the real cv2 SIFT produced).  The only edit of the sources: the hard-coded
-    # /Users/willard/... path prefixes become the relative data/ (sed) -- the same edit oracle/Makefile makes for the CPU build.
+    # /Users/willard/... path prefixes become the relative data/ (sed) -- the same edit the CPU golden build of the tests makes.
     ref_dir = "/root/reference/hnsw_sifts_retrieval"
     o = os.path.join(bdir, "ref_makeSearch_on_b200nn")
     srcs = [os.path.join(ref_dir, "makeSearch.cpp"), os.path.join(ref_dir, "siftsIndex.cpp"), os.path.join(ref_dir, "siftsIndex.hpp")]

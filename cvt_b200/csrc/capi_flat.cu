@@ -103,24 +103,26 @@ int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, vo
         const int groups = u8_scan_tc_lists_per_slice((int)p->dim, (int)k);
         const long long tiles = ((long long)p->n + 255) / 256;
         // Every (slice, group) list pays its own top-k warm-up, and a chunk of accumulators that holds a survivor costs the
-        // epilogue twice what a clean one does.  A large index is therefore scanned in passes of growing size -- 64 tiles
-        // (16 k rows), 8 x as many, then the rest -- and each pass starts from the exact k-th best distance of everything
+        // epilogue far more than a clean one does (a dependent chain of shared-memory loads per survivor).  A large index is
+        // therefore scanned in passes of growing size and each pass starts from the exact k-th best distance of everything
         // before it (an upper bound on the final k-th best; ties are kept, so the result is exact): by the last pass, which
         // holds 7/8 of the rows, the bound sits at a selectivity of k / 131072.
-        long long bounds[4] = {0, tiles, tiles, tiles};
+        long long bounds[5] = {0, tiles, tiles, tiles, tiles};
         int n_pass = 1;
-        if (tiles >= 16 * 64 && !getenv("B200NN_NO_U8_SAMPLE")) {
+        if (tiles >= 1024 && !getenv("B200NN_NO_U8_SAMPLE")) {
+            // 64 tiles (16 k rows), 8 x as many, then the rest.  (A finer schedule -- 16 / 100 / 625 tiles / rest, the first pass
+            // one tile per CTA -- was measured: 0.403 against 0.396 ms for cfg2; every pass has ~15 us of fixed cost.)
             bounds[1] = 64; bounds[2] = 512; bounds[3] = tiles;
             n_pass = 3;
         }
+        auto pass_slices = [&](int ps) { return u8_scan_tc_slices(c->sm_count, (long long)nq, bounds[ps + 1] - bounds[ps], 4); };
         int Lmax = 0;
-        for (int ps = 0; ps < n_pass; ps++)
-            Lmax = std::max(Lmax, u8_scan_tc_slices(c->sm_count, (long long)nq, bounds[ps + 1] - bounds[ps]) * groups + 1);
+        for (int ps = 0; ps < n_pass; ps++) Lmax = std::max(Lmax, pass_slices(ps) * groups + 1);
         if ((rc = p->ws_keys.ensure((size_t)Lmax * nq * k))) return rc;
         if (n_pass > 1 && ((rc = p->ws_thr.ensure(nq * k)) || (rc = p->ws_best.ensure(nq * k)))) return rc;
         for (int ps = 0; ps < n_pass; ps++) {
             const long long t0 = bounds[ps], nt = bounds[ps + 1] - bounds[ps];
-            const int S = u8_scan_tc_slices(c->sm_count, (long long)nq, nt);
+            const int S = pass_slices(ps);
             int L = S * groups;
             if (nt <= 0) B2_CUDA(cudaMemsetAsync(p->ws_keys.p, 0xFF, (size_t)L * nq * k * sizeof(unsigned long long), c->stream));  // empty index
             if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, (long long)p->n, t0, nt, (int)p->dim, (const unsigned char*)q_dev, (long long)nq, S,

@@ -236,7 +236,9 @@ pq_encode_tile_kernel(const float* __restrict__ x, long long n, int D, const flo
     __shared__ __align__(16) float cs[DS * KS];   // [t][codeword]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m = blockIdx.y;
-    const long long row0 = (long long)blockIdx.x * TR;
+    for (int e = tid; e < DS * KS; e += 256) cs[e] = __ldg(cbT + (long long)m * DS * KS + e);  // the codebook of m: staged once per CTA
+    for (long long row0 = (long long)blockIdx.x * TR; row0 < n; row0 += (long long)gridDim.x * TR) {
+    __syncthreads();  // the previous tile's residuals are consumed
     for (int e = tid; e < TR * DS; e += 256) {  // residual sub-vector of row r, element t (runs of DS floats per row)
         const int r = e / DS, t = e - r * DS;
         float v = 0.0f;
@@ -246,7 +248,6 @@ pq_encode_tile_kernel(const float* __restrict__ x, long long n, int D, const flo
         }
         xs[t * XS + r] = v;
     }
-    for (int e = tid; e < DS * KS; e += 256) cs[e] = __ldg(cbT + (long long)m * DS * KS + e);
     __syncthreads();
     float best[8];
     int bidx[8];
@@ -297,6 +298,7 @@ pq_encode_tile_kernel(const float* __restrict__ x, long long n, int D, const flo
         const long long r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (tx == 0 && r < n) codes[r * M + m] = (unsigned char)bidx[i];  // elem.PQindex[i] = vw1, IVFOPQ.cpp:161
     }
+    }  // row tiles of this CTA
 }
 
 }  // namespace
@@ -308,7 +310,9 @@ int launch_pq_encode_tile(Ctx* ctx, const float* x, long long n, int D, const fl
     if (n <= 0) return 0;
     const int ds = D / M;
     if (!pq_encode_tile_supported(ds, ksub)) B2_FAIL(-4, "pq_encode_tile: needs ksub = 256 and D/M in {4, 8, 16}");
-    const dim3 grid((unsigned)((n + 127) / 128), (unsigned)M);
+    // every CTA keeps its sub-quantizer's codebook and walks a strip of row tiles: about 4 CTAs per SM in total
+    const long long tiles = (n + 127) / 128;
+    const dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(tiles, (4LL * ctx->sm_count + M - 1) / M)), (unsigned)M);
     switch (ds) {
         case 4: pq_encode_tile_kernel<4><<<grid, 256, 0, ctx->stream>>>(x, n, D, coarse, list, cbT, M, codes); break;
         case 8: pq_encode_tile_kernel<8><<<grid, 256, 0, ctx->stream>>>(x, n, D, coarse, list, cbT, M, codes); break;

@@ -129,6 +129,90 @@ flat_tile_f32_kernel(const float* __restrict__ x, long long n_rows, int d, const
     }
 }
 
+// A handful of queries (searchKnn is called with ONE: hnsw_sifts_retrieval/makeSearch.cpp:52): the pair tile above would spend
+// 63/64 of its work on padding.  Here the rows stream through shared memory once (coalesced 16-byte loads; the scan is then
+// HBM-bound: n * d * 4 bytes) and L threads share a row, thread l walking elements l, l+L, ... in order for every query --
+// the reference's lane accumulators again -- after which the L partial sums are added left to right by the row's first thread.
+// Row stride d + 4 words puts the 32 (row, lane) pairs of a warp on 32 different banks.
+template <int METRIC, int L, int NQ>
+__global__ void __launch_bounds__(256)
+flat_rows_f32_kernel(const float* __restrict__ x, long long n_rows, int d, const float* __restrict__ q, int nq,
+                     float* __restrict__ dmat /*[nq][ldm]*/, long long ldm) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int RPB = 256 / L;  // rows per pass of the CTA
+    const int RS = d + 4;
+    float* s_q = sm;              // [NQ][d]
+    float* s_x = sm + NQ * d;     // [RPB][RS]
+    const int tid = threadIdx.x, rl = tid / L, l = tid % L;
+    for (int i = tid; i < NQ * d; i += 256) s_q[i] = (i / d < nq) ? q[i] : 0.0f;
+    const int d4 = d >> 2;
+    for (long long r0 = (long long)blockIdx.x * RPB; r0 < n_rows; r0 += (long long)gridDim.x * RPB) {
+        __syncthreads();  // previous pass consumed (and s_q staged)
+        for (int e = tid; e < RPB * d4; e += 256) {
+            const int r = e / d4, c = e - r * d4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < n_rows) v = __ldg(reinterpret_cast<const float4*>(x + (r0 + r) * d) + c);
+            *reinterpret_cast<float4*>(s_x + r * RS + 4 * c) = v;
+        }
+        __syncthreads();
+        float acc[NQ];
+#pragma unroll
+        for (int j = 0; j < NQ; j++) acc[j] = 0.0f;
+        const float* xr = s_x + rl * RS;
+        for (int t = l; t < d; t += L) {
+            const float xv = xr[t];
+#pragma unroll
+            for (int j = 0; j < NQ; j++) {
+                const float qv = s_q[j * d + t];
+                float term;
+                if (METRIC == 0) term = __fmul_rn(qv, xv);
+                else { const float df = __fsub_rn(qv, xv); term = __fmul_rn(df, df); }
+                acc[j] = __fadd_rn(acc[j], term);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NQ; j++) {
+            float sum = acc[j];
+#pragma unroll
+            for (int o = 1; o < L; o++) {  // lanes left to right: ((a0 + a1) + a2) + ...
+                const float v = __shfl_sync(0xffffffffu, acc[j], (threadIdx.x & 31) - l + o);
+                sum = __fadd_rn(sum, v);
+            }
+            if (l == 0 && j < nq && r0 + rl < n_rows) dmat[(long long)j * ldm + r0 + rl] = (METRIC == 0) ? __fsub_rn(1.0f, sum) : sum;
+        }
+    }
+}
+
+template <int METRIC, int L>
+int fr_launch(Ctx* ctx, const float* x, long long rows, int d, const float* q, int nq, float* dmat, long long ldm) {
+    constexpr int NQ = 4;
+    const size_t smem = ((size_t)NQ * d + (size_t)(256 / L) * (d + 4)) * sizeof(float);
+    if (smem > 200 * 1024) return -100;  // caller falls back to the pair tile
+    if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(flat_rows_f32_kernel<METRIC, L, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long passes = (rows + 256 / L - 1) / (256 / L);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(passes, (long long)ctx->sm_count * 4));
+    for (int q0 = 0; q0 < nq; q0 += NQ) {
+        flat_rows_f32_kernel<METRIC, L, NQ><<<grid, 256, smem, ctx->stream>>>(x, rows, d, q + (size_t)q0 * d, std::min(NQ, nq - q0), dmat + (size_t)q0 * ldm, ldm);
+        ctx->launches++;
+    }
+    B2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fr_dispatch(Ctx* ctx, int metric, int order, const float* x, long long rows, int d, const float* q, int nq, float* dmat, long long ldm) {
+    if (d % 4 != 0 || d % order != 0) return -100;
+    if (metric == 0) {
+        if (order == 1) return fr_launch<0, 1>(ctx, x, rows, d, q, nq, dmat, ldm);
+        if (order == 4) return fr_launch<0, 4>(ctx, x, rows, d, q, nq, dmat, ldm);
+        if (order == 8) return fr_launch<0, 8>(ctx, x, rows, d, q, nq, dmat, ldm);
+    } else if (metric == 1) {
+        if (order == 1) return fr_launch<1, 1>(ctx, x, rows, d, q, nq, dmat, ldm);
+        if (order == 4) return fr_launch<1, 4>(ctx, x, rows, d, q, nq, dmat, ldm);
+        if (order == 8) return fr_launch<1, 8>(ctx, x, rows, d, q, nq, dmat, ldm);
+    }
+    return -100;
+}
+
 template <int METRIC, int L, int TI, int TJ>
 int ft_launch(Ctx* ctx, const float* x, long long rows, int d, const float* q, long long nq, float* dmat, long long ldm) {
     dim3 grid((unsigned)((rows + 16 * TI - 1) / (16 * TI)), (unsigned)((nq + 16 * TJ - 1) / (16 * TJ)));
@@ -182,7 +266,10 @@ int launch_flat_scan_f32(Ctx* ctx, int metric, int order, const float* data, con
             B2_CUDA(cudaMemsetAsync(out_keys + (size_t)c * S * nq * k, 0xFF, (size_t)S * nq * k * sizeof(unsigned long long), ctx->stream));
             continue;
         }
-        if ((rc = ft_dispatch(ctx, metric, order, data + r0 * d, rows, d, queries, nq, ctx->dmat, cr))) return rc;
+        rc = -100;
+        if (nq <= 8) rc = fr_dispatch(ctx, metric, order, data + r0 * d, rows, d, queries, (int)nq, ctx->dmat, cr);  // streaming kernel for a few queries
+        if (rc == -100) rc = ft_dispatch(ctx, metric, order, data + r0 * d, rows, d, queries, nq, ctx->dmat, cr);
+        if (rc) return rc;
         if ((rc = launch_dense_topk_ex(ctx, ctx->dmat, nq, rows, cr, k, S, rank + r0, out_keys + (size_t)c * S * nq * k))) return rc;
     }
     return 0;

@@ -846,20 +846,30 @@ ivf_search_topk_kernel(const float* __restrict__ q_rot, long long nq, int D, con
     }
     flush_all();
     __syncthreads();
+    // Fewer than k probed rows scored below the clamp: the tail is (clamp, smallest ids not already in the list), IVFOPQ.cpp:369 +
+    // common.h:25-37.  The list holds real < k records, so among the ids [0, 2k) at least k are absent: thread t < 2k tests id t
+    // against the list, a ballot/prefix count gives every absent id its slot.
+    __shared__ int s_real, s_wcnt[8];
     if (w == 0) {
-        // how many real records, then fill with (clamp, smallest ids not already present)
         int real = 0;
         for (int j = lane; j < k; j += 32) real += (s_list[j] != KEY_MAX) ? 1 : 0;
 #pragma unroll
         for (int sft = 16; sft >= 1; sft >>= 1) real += __shfl_xor_sync(0xffffffffu, real, sft);
-        if (real < k && lane == 0) {
-            int filled = real;
-            for (long long id = 0; id < n_rows && filled < k; id++) {
-                bool present = false;
-                for (int j = 0; j < real; j++) present |= ((uint32_t)(s_list[j] & 0xFFFFFFFFull) == id_base + (uint32_t)id);
-                if (!present) s_list[filled++] = make_key(clamp_ord, id_base + (uint32_t)id);
-            }
-        }
+        if (lane == 0) s_real = real;
+    }
+    __syncthreads();
+    const int real = s_real;
+    if (real < k) {  // CTA-uniform
+        const int t = threadIdx.x;  // 256 threads >= 2k
+        bool absent = t < 2 * k && (long long)t < n_rows;
+        if (absent)
+            for (int j = 0; j < real; j++) absent &= ((uint32_t)(s_list[j] & 0xFFFFFFFFull) != id_base + (uint32_t)t);
+        const unsigned msk = __ballot_sync(0xffffffffu, absent);
+        if (lane == 0) s_wcnt[w] = __popc(msk);
+        __syncthreads();
+        int before = __popc(msk & ((1u << lane) - 1));
+        for (int i = 0; i < w; i++) before += s_wcnt[i];
+        if (absent && real + before < k) s_list[real + before] = make_key(clamp_ord, id_base + (uint32_t)t);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < k; j += blockDim.x) out_keys[q * k + j] = s_list[j];

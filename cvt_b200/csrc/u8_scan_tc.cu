@@ -27,6 +27,7 @@
 // Supported: D % 32 == 0, D <= 256, k <= 120 as far as the lists fit shared memory beside the operand tiles (k <= 120 at
 // D = 128 with one epilogue group); otherwise the dp4a kernel of flat_kernels.cu is used.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -330,7 +331,10 @@ static size_t tc_smem_bytes(int D, int k, int groups, int stages) {
     return (size_t)TC_M * D + (size_t)stages * TC_N * D + (size_t)(stages + 2) * TC_META_BYTES +
            (size_t)groups * (TC_M * (size_t)k * 8 + 4 * 32 * 32 * 4) + TC_M * 4 + 256;
 }
-// two epilogue groups when their lists and scratch fit beside the operand tiles, else one
+// Two epilogue groups when their lists and scratch fit beside the operand tiles, else one.  (Four groups -- 16 epilogue warps,
+// 64 accumulator columns each -- were measured: the bulk pass of cfg2 went from 233 to 223 us only, because the drain is
+// bound by the TMEM read port, 64 B/clk per SM = 2048 clk for the 128 KB of int32 accumulators of a tile, not by issue or
+// latency; the extra lists made the merges dearer than that gain.)
 int u8_scan_tc_lists_per_slice(int D, int k) { return tc_smem_bytes(D, k, 2, 2) <= (size_t)TC_MAX_SMEM ? 2 : 1; }
 
 bool u8_scan_tc_supported(int D, int k) {
@@ -348,10 +352,10 @@ int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint3
     return 0;
 }
 
-int u8_scan_tc_slices(int sm_count, long long nq, long long n_tiles) {
+int u8_scan_tc_slices(int sm_count, long long nq, long long n_tiles, int min_tiles_per_slice) {
     const long long qt = (nq + TC_M - 1) / TC_M, tiles = n_tiles;
     long long s = sm_count / qt;  // one wave of one-CTA-per-SM
-    s = std::max<long long>(1, std::min<long long>(s, std::max<long long>(1, tiles / 4)));
+    s = std::max<long long>(1, std::min<long long>(s, std::max<long long>(1, tiles / std::max(1, min_tiles_per_slice))));
     return (int)std::min<long long>(s, 1024);
 }
 

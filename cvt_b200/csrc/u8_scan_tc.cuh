@@ -9,7 +9,8 @@ bool u8_scan_tc_supported(int D, int k);
 // (n_pad = multiple of 256; xmeta holds 2 * n_pad ints)
 int launch_u8_rows_to_canonical(Ctx* ctx, const unsigned char* rows, const uint32_t* rank, long long n, int D, unsigned char* xcan,
                                 int* xmeta, long long n_pad);
-int u8_scan_tc_slices(int sm_count, long long nq, long long n_tiles);  // row slices for a pass over n_tiles tiles of 256 rows
+// row slices for a pass over n_tiles tiles of 256 rows (one wave of CTAs, at least min_tiles_per_slice tiles each)
+int u8_scan_tc_slices(int sm_count, long long nq, long long n_tiles, int min_tiles_per_slice = 4);
 int u8_scan_tc_lists_per_slice(int D, int k);
 // out_keys [n_slices * u8_scan_tc_lists_per_slice(D, k)][nq][k]; ids in the keys are label ranks.
 // init_thr (may be NULL): init_thr[q * init_stride] = an upper bound on query q's k-th best distance, e.g. the k-th

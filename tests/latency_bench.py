@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small-batch / per-call latencies of the entry points the reference interface forces, next to the
 reference's own CPU code on the same inputs (oracle/_ref, per-call time = difference of two runs so that load/build time
-cancels).  Development aid; prints one JSON document.
+cancels).  Development aid (lives under tests/ because it times the CPU checker binaries); prints one JSON document.
 
   makeSearch shape   125 402 x 128 rootSIFT rows (hnsw_sifts_retrieval/makeIdx.cpp:303-309), 1 536 descriptors, k = 5, 1 - <a,b>:
                      one batch (searchKnnBatch) and one query per call (searchKnn as makeSearch.cpp:52 calls it)

@@ -14,5 +14,5 @@ try:
     l=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print("cfg2: qps %.0f ms %.3f frac %.3f" % (l["value"], l["ms_per_step"], l["roofline"]["frac"]), l.get("parity"))
 except Exception as e: print("cfg2 unreadable", e)
 PY
-timeout 600 python tools/latency_bench.py > "$out/${tag}_latency.json" 2> "$out/${tag}_latency.err"; cat "$out/${tag}_latency.json"; tail -c 300 "$out/${tag}_latency.err"
+timeout 600 python tests/latency_bench.py > "$out/${tag}_latency.json" 2> "$out/${tag}_latency.err"; cat "$out/${tag}_latency.json"; tail -c 300 "$out/${tag}_latency.err"
 timeout 120 python tools/quick_ivf_bench.py > "$out/${tag}_ivf_bench.txt" 2>&1; tail -n 6 "$out/${tag}_ivf_bench.txt"

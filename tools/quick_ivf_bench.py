@@ -29,8 +29,12 @@ dt = time.perf_counter() - t0
 print(f"IVFOPQ::Add of {n} rows from host memory (rotate + coarse assign + residual PQ encode): {dt:.3f} s = {n / dt / 1e6:.2f} M rows/s")
 idx.search(q[:256], k, nprobe=3)
 for nprobe in (1, 3, 8):
-    t0 = time.perf_counter()
-    d, i = idx.search(q, k, nprobe=nprobe)
-    dt = time.perf_counter() - t0
+    idx.search(q, k, nprobe=nprobe)  # workspaces of this shape
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        d, i = idx.search(q, k, nprobe=nprobe)
+        ts.append(time.perf_counter() - t0)
+    dt = sorted(ts)[2]
     found = float((i < n).mean())
     print(f"IVF search {nq} queries, top-{k}, nprobe={nprobe}: {dt * 1e3:.2f} ms = {nq / dt / 1e3:.0f} k QPS (host buffers); filled result slots {found:.3f}")
