@@ -96,7 +96,18 @@ def main():
     one = v[:1].copy()
     t1 = wall(lambda: sq.encode(one, l2norm=True), 300, warm=20)
     tb = wall(lambda: sq.encode(v, l2norm=True), 50)
-    out["int8_encode"] = {"single_vector_call_us": 1e6 * t1, "batch_4096_us_per_vector": 1e6 * tb / 4096}
+    cpu_enc = None
+    try:  # the reference's Int8Quan::Int8Encode on the host: per-vector time = difference of two runs of the reference-run driver
+        from oracle import oracle as orc
+        if orc.have_ref("ref_int8_quan"):
+            big = synth.sift_like(200_000, 128, seed=15)
+            t0 = time.perf_counter(); orc.run_ref_int8_quan(big[:1000], vmin, vdiff); ta = time.perf_counter() - t0
+            t0 = time.perf_counter(); orc.run_ref_int8_quan(big, vmin, vdiff); tb2 = time.perf_counter() - t0
+            cpu_enc = (tb2 - ta) / (len(big) - 1000) / 4.0   # the driver runs encode, normalise, decode and the faiss-path encode per row
+    except Exception:
+        pass
+    out["int8_encode"] = {"single_vector_call_us": 1e6 * t1, "batch_4096_us_per_vector": 1e6 * tb / 4096,
+                          "cpu_reference_us_per_vector_approx": None if cpu_enc is None else 1e6 * cpu_enc}
     sq.close()
     # ---- IVFOPQ::Query, 8 frames
     n = 20_000
@@ -108,8 +119,27 @@ def main():
     frames = synth.sift_like(8, 128, seed=13)
     t8 = wall(lambda: pq.scores(frames, nprobe=3), 100, warm=10)
     t64 = wall(lambda: pq.search(synth.sift_like(64, 128, seed=14), 100, nprobe=1), 50, warm=5)
+    cpu_q = None
+    try:  # the unmodified IVFOPQ::QueryThrehold + get_sort_results on the host, 1 thread, 8 frames
+        import shutil
+        from oracle import oracle as orc
+        if orc.have_ref("ref_opq"):
+            td = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            try:
+                synth.write_opq_model(os.path.join(td, "m.model"), coarse, cb, perm)
+                synth.write_feat_file(os.path.join(td, "db.bin"), db)
+                synth.write_feat_file(os.path.join(td, "q.bin"), frames)
+                r = orc.bench_ref_opq(os.path.join(td, "m.model"), os.path.join(td, "db.bin"), os.path.join(td, "q.bin"), nk=3, topk=5,
+                                      n_queries=8, threads=1, tmpdir=td, repeat=5)
+                cpu_q = r["query_s_mean"]
+            finally:
+                shutil.rmtree(td, ignore_errors=True)
+    except Exception:
+        pass
     out["ivfopq_query"] = {"rows": n, "K": 256, "groups": pq.n_groups, "frames": 8, "query_8_frames_us": 1e6 * t8,
-                           "search_64_queries_top100_nprobe1_us": 1e6 * t64}
+                           "search_64_queries_top100_nprobe1_us": 1e6 * t64,
+                           "cpu_reference_query_8_frames_us": None if cpu_q is None else 1e6 * cpu_q,
+                           "cpu_note": "reference index with one videoId per ROW (20 000 groups), 1 thread; the GPU index has 1 000 videos"}
     pq.close()
     ctx.close()
     print(json.dumps(out, indent=1))

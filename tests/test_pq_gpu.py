@@ -315,3 +315,41 @@ def test_coarse_assign_and_probes_large_K_tiled(ctx):
     for i in range(nq):
         assert np.array_equal(probes[i], orc.opq_coarse_probe(qr[i], coarse, nk)), i
     idx.close()
+
+
+def test_reference_index_shape_K8192_end_to_end(ctx):
+    """The reference's real index shape on the GPU: K = 8192 coarse centroids, M = 16, D = 128, nprobe = 3 (the shipped
+    opq/model/*_k_8192_PQ_m16_k256_reorder.model has exactly this shape; the model file itself stays in /root/reference, so the
+    centroids here are seeded).  Add -> coarse lists + codes, QueryThrehold scores per videoId and the fused top-k search are
+    compared with the restatement bit for bit."""
+    from cvt_b200 import capi
+    D, M, K, n, nq, nk, k = 128, 16, 8192, 12_000, 24, 3, 40
+    rng = np.random.Generator(np.random.PCG64(8192))
+    x = synth.sift_like(n, D, seed=81)
+    q = np.concatenate([x[:8] * np.float32(1.0), synth.sift_like(nq - 8, D, seed=82)])   # 8 queries are database rows
+    perm = synth.SHIPPED_REORDER_128
+    coarse = np.concatenate([x[rng.choice(n, 4096, replace=False)][:, perm],
+                             synth.sift_like(4096, D, seed=83)[:, perm]]).astype(np.float32)
+    cb = (rng.standard_normal((M, 256, D // M)) * 0.03).astype(np.float32)
+    groups = (np.arange(n) // 12).astype(np.int32)
+    idx = capi.PQIndex.create(ctx, coarse, cb, perm=perm, clamp=1.0)
+    idx.add(x, groups)
+    lists, grp, codes = idx.get_rows()
+    xr = orc.opq_reorder(x, perm)
+    ol = orc.opq_coarse_assign(xr, coarse)
+    assert np.array_equal(lists, ol) and np.array_equal(grp, groups)
+    assert np.array_equal(codes, orc.opq_pq_encode(xr, coarse, ol, cb))
+    qr = orc.opq_reorder(q, perm)
+    S = idx.scores(q, nprobe=nk)
+    So = orc.opq_query_scores(qr, coarse, cb, nk, lists, groups, codes, idx.n_groups, 1.0)
+    assert np.array_equal(_bits(S), _bits(So))
+    assert (S[:8].min(axis=1) < 0.5).all()       # a database row finds its own video
+    idx2 = capi.PQIndex.create(ctx, coarse, cb, perm=perm, clamp=1.0)
+    idx2.add(x)                                   # videoId = row: the per-vector top-k path
+    Dg, Ig = idx2.search(q, k, nprobe=nk)
+    dense = orc.opq_query_scores(qr, coarse, cb, nk, lists, np.arange(n, dtype=np.int32), codes, n, 1.0)
+    for i in range(nq):
+        os_, oi = orc.topk_pairs(dense[i], k)
+        assert np.array_equal(Ig[i].astype(np.int64), oi), i
+        assert np.array_equal(_bits(Dg[i]), _bits(os_)), i
+    idx.close(); idx2.close()
