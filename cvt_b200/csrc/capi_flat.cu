@@ -30,6 +30,7 @@ struct b200nn_flat {
     long long tc_rows = -1;
     DevBuf<unsigned char> xcan;
     DevBuf<int> xnorm;   // per-tile row meta: |x|^2 and label rank
+    DevBuf<int> ws_gmin;  // [nq][32] list minima of the one-pass shared-bound scan
     DevBuf<int> ws_thr;  // [nq][k] distances of the sample pass (column k-1 = the bound the full pass starts from)
     DevBuf<unsigned char> ws_q;
     DevBuf<unsigned long long> ws_keys, ws_id, ws_best;  // ws_best: the best k of the passes so far (sorted keys)
@@ -109,7 +110,14 @@ int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, vo
         // holds 7/8 of the rows, the bound sits at a selectivity of k / 131072.
         long long bounds[5] = {0, tiles, tiles, tiles, tiles};
         int n_pass = 1;
-        if (tiles >= 1024 && !getenv("B200NN_NO_U8_SAMPLE")) {
+        // One pass with a shared bound (u8_scan_tc.cu, the bound warp) when a query has at least k lists to take minima from:
+        // no pass structure, no intermediate merges, the lists live through the whole scan.
+        const int S_all = u8_scan_tc_slices(c->sm_count, (long long)nq, tiles, 4);
+        const bool shared_bound = tiles >= 1024 && (int)k <= std::min(u8_scan_tc_bound_lists(), S_all * groups) && !getenv("B200NN_U8_NO_SHARED_BOUND");
+        if (shared_bound) {
+            if ((rc = p->ws_gmin.ensure(nq * (size_t)u8_scan_tc_bound_lists()))) return rc;
+            B2_CUDA(cudaMemsetAsync(p->ws_gmin.p, 0x7f, nq * (size_t)u8_scan_tc_bound_lists() * sizeof(int), c->stream));
+        } else if (tiles >= 1024 && !getenv("B200NN_NO_U8_SAMPLE")) {
             // 64 tiles (16 k rows), 8 x as many, then the rest.  (A finer schedule -- 16 / 100 / 625 tiles / rest, the first pass
             // one tile per CTA -- was measured: 0.403 against 0.396 ms for cfg2; every pass has ~15 us of fixed cost.)
             bounds[1] = 64; bounds[2] = 512; bounds[3] = tiles;
@@ -126,7 +134,7 @@ int search_dev_locked(b200nn_flat* p, const void* q_dev, size_t nq, size_t k, vo
             int L = S * groups;
             if (nt <= 0) B2_CUDA(cudaMemsetAsync(p->ws_keys.p, 0xFF, (size_t)L * nq * k * sizeof(unsigned long long), c->stream));  // empty index
             if ((rc = launch_u8_scan_tc(c, p->xcan.p, p->xnorm.p, (long long)p->n, t0, nt, (int)p->dim, (const unsigned char*)q_dev, (long long)nq, S,
-                                        (int)k, ps ? p->ws_thr.p + (k - 1) : nullptr, (int)k, p->ws_keys.p)))
+                                        (int)k, ps ? p->ws_thr.p + (k - 1) : nullptr, (int)k, shared_bound ? p->ws_gmin.p : nullptr, p->ws_keys.p)))
                 return rc;
             if (ps) {  // the best k of the earlier passes ride along as one more list
                 B2_CUDA(cudaMemcpyAsync(p->ws_keys.p + (size_t)L * nq * k, p->ws_best.p, nq * k * sizeof(unsigned long long), cudaMemcpyDeviceToDevice,

@@ -236,37 +236,54 @@ __global__ void lut_build_scan_kernel(const float* __restrict__ q, long long nq,
     }
     __syncthreads();
     float* out = lut_scan + qg * 32768;
-    // blockIdx.y = which slice of the group's 32768 entries: more CTAs than query groups, so that a small batch
-    // (one rank's chunk of a sharded batch) still fills the machine
-    const int e_per = 32768 / (int)gridDim.y;
-    for (int e = (int)blockIdx.y * e_per + threadIdx.x; e < ((int)blockIdx.y + 1) * e_per; e += blockDim.x) {
-        const int lane = e & 31, msel = (e >> 5) & 1, j = (e >> 6) & 255, pair = e >> 14;
-        const int h = lane / QW, ql = lane - h * QW;
-        const int m = 4 * h + 2 * pair + msel;
+    // One thread = one codeword (m, j) against all QW queries of the group: the codeword row is loaded once (lanes read
+    // consecutive rows), the residual sub-vectors are warp-uniform shared-memory broadcasts, and the QW results are
+    // adjacent in the scan layout (one run of QW floats).  blockIdx.y = which slice of the M*256 codewords: more CTAs than
+    // query groups, so that a small batch (one rank's chunk of a sharded batch) still fills the machine.
+    const int t_per = M * 256 / (int)gridDim.y;
+    for (int t = (int)blockIdx.y * t_per + threadIdx.x; t < ((int)blockIdx.y + 1) * t_per; t += blockDim.x) {
+        const int m = t >> 8, j = t & 255;
+        const int h = m >> 2, pair = (m >> 1) & 1, msel = m & 1;
         const float* c = cb + ((long long)m * 256 + j) * DS;
-        const float* r = s_res + ql * RS + m * DS;
-        float acc = 0.0f;
-        if (DS % 4 == 0) {  // 16-byte loads: codeword row (read-only path) and residual (shared)
+        float cv[DS];
+        if (DS % 4 == 0) {
 #pragma unroll
             for (int k = 0; k < DS; k += 4) {
-                const float4 cv = __ldg(reinterpret_cast<const float4*>(c + k));
-                const float4 rv = *reinterpret_cast<const float4*>(r + k);
-                float t;
-                t = __fsub_rn(rv.x, cv.x); acc = __fadd_rn(acc, __fmul_rn(t, t));
-                t = __fsub_rn(rv.y, cv.y); acc = __fadd_rn(acc, __fmul_rn(t, t));
-                t = __fsub_rn(rv.z, cv.z); acc = __fadd_rn(acc, __fmul_rn(t, t));
-                t = __fsub_rn(rv.w, cv.w); acc = __fadd_rn(acc, __fmul_rn(t, t));
+                const float4 v = __ldg(reinterpret_cast<const float4*>(c + k));
+                cv[k] = v.x; cv[k + 1] = v.y; cv[k + 2] = v.z; cv[k + 3] = v.w;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < DS; k++) {
-                const float t = __fsub_rn(r[k], __ldg(c + k));
-                acc = __fadd_rn(acc, __fmul_rn(t, t));
-            }
+            for (int k = 0; k < DS; k++) cv[k] = __ldg(c + k);
         }
-        out[e] = (qg * QW + ql < nq) ? acc : 0.0f;
+        float acc[QW];
+#pragma unroll
+        for (int ql = 0; ql < QW; ql++) {
+            const float* r = s_res + ql * RS + m * DS;
+            float a = 0.0f;
+            if (DS % 4 == 0) {
+#pragma unroll
+                for (int k = 0; k < DS; k += 4) {
+                    const float4 rv = *reinterpret_cast<const float4*>(r + k);
+                    float d;
+                    d = __fsub_rn(rv.x, cv[k]); a = __fadd_rn(a, __fmul_rn(d, d));
+                    d = __fsub_rn(rv.y, cv[k + 1]); a = __fadd_rn(a, __fmul_rn(d, d));
+                    d = __fsub_rn(rv.z, cv[k + 2]); a = __fadd_rn(a, __fmul_rn(d, d));
+                    d = __fsub_rn(rv.w, cv[k + 3]); a = __fadd_rn(a, __fmul_rn(d, d));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < DS; k++) {
+                    const float d = __fsub_rn(r[k], cv[k]);
+                    a = __fadd_rn(a, __fmul_rn(d, d));
+                }
+            }
+            acc[ql] = (qg * QW + ql < nq) ? a : 0.0f;
+        }
+        float4* o4 = reinterpret_cast<float4*>(out + pair * 16384 + j * 64 + msel * 32 + h * QW);
+#pragma unroll
+        for (int ql = 0; ql < QW; ql += 4) o4[ql >> 2] = make_float4(acc[ql], acc[ql + 1], acc[ql + 2], acc[ql + 3]);
     }
-    (void)M;
 }
 
 // =============================================================================================
@@ -297,13 +314,18 @@ __global__ void lut_build_scan_kernel(const float* __restrict__ q, long long nq,
 // a per-warp staging buffer and are merged into the CTA's sorted per-query list (topk.cuh).
 // Each CTA emits k sorted keys per query; topk_merge_kernel merges the slices.
 // =============================================================================================
-template <int G, int WARPS_>
+// VAR bit 1 (grouped check): the threshold test is made once per 4 blocks instead of once per block (see group_body).
+// VAR bit 0 (used for G = 8, where three 64-row stages of 8 planes per warp do not fit beside the LUT): a ring of TWO
+// whole-granule stages whose prefetch is issued in the MIDDLE of the current stage, once the lagging lane groups
+// (G-1 <= 8 blocks behind) have left the previous one -- half as many TMA copies (256 B instead of 128 B each) and half
+// as many stage boundaries per row as the three 32-row stages of VAR = 0.
+template <int G, int WARPS_, int VAR = 0>
 struct ScanCfg {
     static constexpr int QW = 32 / G;                          // queries per CTA
     static constexpr int WARPS = WARPS_;
-    static constexpr int STAGE_BLOCKS = (G <= 4) ? 16 : 8;     // blocks (of 4 rows) per ring stage (> G-1 lag)
+    static constexpr int STAGE_BLOCKS = (G <= 4 || (VAR & 1)) ? 16 : 8;     // blocks (of 4 rows) per ring stage (> G-1 lag)
     static constexpr int STAGE_ROWS = STAGE_BLOCKS * 4;
-    static constexpr int RING_STAGES = 3;                      // previous (lagging lane groups) | current | prefetch
+    static constexpr int RING_STAGES = (VAR & 1) ? 2 : 3;     // previous (lagging lane groups) | current | prefetch
     static constexpr int PLANE_RING_BYTES = RING_STAGES * STAGE_ROWS * 4;  // per lane group
     static constexpr int RING_BYTES = G * PLANE_RING_BYTES;                // per warp
     // staging records per (warp, query): as many as shared memory allows (99 KB beside the LUT)
@@ -317,7 +339,7 @@ struct ScanCfg {
     // parked in global scratch and the CTA then selects their top-k in one dense pass (lanes over rows),
     // which is far cheaper per record than the streaming candidate path that a k(1+ln(n/k)) warm-up
     // would otherwise take for exactly these rows.
-    static constexpr int WARM_STAGES = (G <= 4) ? 2 : 4;
+    static constexpr int WARM_STAGES = (STAGE_BLOCKS == 16) ? 2 : 4;
     static constexpr int WARM_BLOCKS = WARM_STAGES * STAGE_BLOCKS;   // 32 blocks = 128 rows per warp
     static constexpr int WARM_ROWS = WARM_BLOCKS * 4;
     static constexpr int LUT_BYTES = 131072;
@@ -347,7 +369,7 @@ __device__ __forceinline__ float lds_f32_off(uint32_t addr) {
 // Every (query, segment) pair pays a top-k warm-up of ~k(1 + ln(rows/k)) insertions, so pieces are
 // used only where they buy balance.  tail_desc holds two {group, slice, granule lo, granule hi}
 // records per tail CTA (scan_plan); the second is empty (lo >= hi) when the piece lies in one group.
-template <int G, int WARPS_, bool STATS>
+template <int G, int WARPS_, bool STATS, int VAR = 0>
 __global__ void __launch_bounds__(WARPS_ * 32, 1)
 adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                      const float* __restrict__ lut_scan,    // [qgroups][32768]
@@ -360,7 +382,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
                      int soft_thr,                               // staged records at which a warp tries to merge
                      unsigned long long* __restrict__ stats,     // STATS builds only (B200NN_SCAN_STATS): counters, see scan_launch
                      int* __restrict__ err_flag) {
-    using C = ScanCfg<G, WARPS_>;
+    using C = ScanCfg<G, WARPS_, VAR>;
     constexpr int QW = C::QW;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -511,7 +533,7 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
         }
     };
 
-    auto rare_path = [&](int Bg, float mn) {
+    auto rare_path = [&](int Bg, float mn, float o0, float o1, float o2, float o3) {  // the block's four final scores
         // Bg = block counter of lane group 0; this lane's block is Bg - h.  Only lanes of the last
         // lane group can satisfy mn <= tau (tau = -inf elsewhere).
         if (mn <= tau && Bg - h >= warm_nblocks) {  // blocks below warm_nblocks were parked and selected in phase B
@@ -569,16 +591,70 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
             const int Bh = Bg - (G - 1);
             if (last_group && (unsigned)Bh < (unsigned)warm_nblocks)
                 *reinterpret_cast<float4*>(my_scratch + Bh * 4) = make_float4(s0, s1, s2, s3);
-        } else {
+        } else if constexpr (!(VAR & 2)) {
             const float mn = fminf(fminf(s0, s1), fminf(s2, s3));
             if (__any_sync(0xffffffffu, mn <= tau)) {
                 if (STATS) st_ev++;
-                rare_path(Bg, mn);
+                rare_path(Bg, mn, s0, s1, s2, s3);
             }
         }
     };
+    // Grouped check (VAR bit 1): four blocks are computed back to back and their 16 final scores stay in registers; ONE
+    // vote + branch per group decides whether any of them meets the threshold.  The hot loop is then 4 straight-line
+    // block bodies (the loads of a block overlap the add chains of the one before, nothing to serialise on) and a single
+    // out-of-line copy of the candidate path, which walks the group's blocks in order.
+    float ga0, ga1, ga2, ga3, gb0, gb1, gb2, gb3, gc0, gc1, gc2, gc3;  // scores of a group's first three blocks (the fourth: o0..o3)
+    float gma, gmb, gmc, gmd;                                          // the four blocks' minima
+    auto group_compute = [&](int Bg0) -> float {
+        block_body(Bg0, std::false_type{}); ga0 = o0; ga1 = o1; ga2 = o2; ga3 = o3;
+        block_body(Bg0 + 1, std::false_type{}); gb0 = o0; gb1 = o1; gb2 = o2; gb3 = o3;
+        block_body(Bg0 + 2, std::false_type{}); gc0 = o0; gc1 = o1; gc2 = o2; gc3 = o3;
+        block_body(Bg0 + 3, std::false_type{});
+        gma = fminf(fminf(ga0, ga1), fminf(ga2, ga3));
+        gmb = fminf(fminf(gb0, gb1), fminf(gb2, gb3));
+        gmc = fminf(fminf(gc0, gc1), fminf(gc2, gc3));
+        gmd = fminf(fminf(o0, o1), fminf(o2, o3));
+        return fminf(fminf(gma, gmb), fminf(gmc, gmd));
+    };
+    auto group_rare = [&](int Bg0) {  // visits, in order, the blocks of the group that hold a candidate (one copy of the candidate path)
+        // which blocks: four independent votes up front (a flush on the way can only tighten tau; rare_path re-tests per lane)
+        unsigned hits = (__any_sync(0xffffffffu, gma <= tau) ? 1u : 0u) | (__any_sync(0xffffffffu, gmb <= tau) ? 2u : 0u) |
+                        (__any_sync(0xffffffffu, gmc <= tau) ? 4u : 0u) | (__any_sync(0xffffffffu, gmd <= tau) ? 8u : 0u);
+#pragma unroll 1
+        while (hits) {
+            const int u = __ffs(hits) - 1;
+            hits &= hits - 1;
+            if (STATS) st_ev++;
+            const float s0 = (u == 0) ? ga0 : (u == 1) ? gb0 : (u == 2) ? gc0 : o0;
+            const float s1 = (u == 0) ? ga1 : (u == 1) ? gb1 : (u == 2) ? gc1 : o1;
+            const float s2 = (u == 0) ? ga2 : (u == 1) ? gb2 : (u == 2) ? gc2 : o2;
+            const float s3 = (u == 0) ? ga3 : (u == 1) ? gb3 : (u == 2) ? gc3 : o3;
+            rare_path(Bg0 + u, fminf(fminf(s0, s1), fminf(s2, s3)), s0, s1, s2, s3);
+        }
+    };
+    int Bg = 0;
+    // a run of blocks (a multiple of 4)
+    auto run_blocks = [&](int nb, auto warm_tag) {
+        if constexpr ((VAR & 2) && !decltype(warm_tag)::value) {
+            // the inner loop is the hot path: straight-line group, vote, a forward branch that is normally NOT taken
+            int bb = 0;
+            while (bb < nb) {
+                bool hit;
+#pragma unroll 1
+                do {
+                    const float mn = group_compute(Bg);
+                    bb += 4; Bg += 4;
+                    hit = __any_sync(0xffffffffu, mn <= tau);
+                } while (!hit && bb < nb);
+                if (hit) group_rare(Bg - 4);
+            }
+        } else {
+#pragma unroll 4
+            for (int bb = 0; bb < nb; bb++, Bg++) block_body(Bg, warm_tag);
+        }
+    };
 
-    int Bg = 0, slot = 0, st = 0;
+    int slot = 0, st = 0;
     auto next_stage = [&]() {
         const int next = (slot == C::RING_STAGES - 1) ? 0 : slot + 1;
         // the slot after the current one held stage st-2, which every lane group has left
@@ -587,12 +663,28 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
         phases ^= 1u << slot;
         slot = next;
     };
+    // one stage of blocks; VAR = 1: two-slot ring, the next stage is requested in the middle of this one
+    auto run_stage = [&](auto warm_tag, bool refresh) {
+        if constexpr (!(VAR & 1)) {
+            next_stage();
+            if (refresh) refresh_tau();
+            run_blocks(C::STAGE_BLOCKS, warm_tag);
+        } else {
+            constexpr int HALF = C::STAGE_BLOCKS / 2;
+            static_assert(HALF >= G - 1, "the lagging lane groups must have left the previous stage at the half-way point");
+            mbar_wait(full_bar + 8 * slot, (phases >> slot) & 1u);
+            phases ^= 1u << slot;
+            if (refresh) refresh_tau();
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {  // one copy of the unrolled body (instruction cache)
+                if (half == 1 && st + 1 < n_st) issue_stage(st + 1, slot ^ 1);
+                run_blocks(HALF, warm_tag);
+            }
+            slot ^= 1;
+        }
+    };
     // ---- phase A: warm-up stages, scores parked ----
-    for (; st < min(n_st, C::WARM_STAGES); st++) {
-        next_stage();
-#pragma unroll 4
-        for (int bb = 0; bb < C::STAGE_BLOCKS; bb++, Bg++) block_body(Bg, std::true_type{});
-    }
+    for (; st < min(n_st, C::WARM_STAGES); st++) run_stage(std::true_type{}, false);
     // ---- phase B: the CTA selects the top-k of all parked rows in one dense pass ----
     if (lane == 0) {
         warm_valid[w] = min((uint32_t)warm_nblocks * 4u, nrel);
@@ -635,10 +727,12 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
             uint32_t lo = vmin, hi = vmax;
             while (lo < hi) {
                 const uint32_t mid = lo + ((hi - lo) >> 1);
-                uint32_t c = 0;
+                // four independent predicated counters: one dependent add per 4 elements instead of a 2-op chain per element
+                uint32_t c4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                for (int i = 0; i < E; i++) c += (x[i] <= mid) ? 1u : 0u;
-                c = __reduce_add_sync(0xffffffffu, c);
+                for (int i = 0; i < E; i++)
+                    asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(c4[i & 3]) : "r"(x[i]), "r"(mid));
+                const uint32_t c = __reduce_add_sync(0xffffffffu, (c4[0] + c4[1]) + (c4[2] + c4[3]));
                 if (c >= kk) hi = mid; else lo = mid + 1;
             }
             const uint32_t v = lo;
@@ -647,30 +741,38 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
             for (int i = 0; i < E; i++) { c_lt += (x[i] < v) ? 1u : 0u; c_le += (x[i] <= v) ? 1u : 0u; }
             c_lt = __reduce_add_sync(0xffffffffu, c_lt);
             c_le = __reduce_add_sync(0xffffffffu, c_le);
-            uint32_t tmax = NONE;  // ties at v are kept while id <= tmax
-            if (c_le > kk) {       // tied k-th score: the smallest ids win (warp-uniform branch)
-                const uint32_t need = kk - c_lt;
-                uint32_t ilo = 0, ihi = NONE;
-                while (ilo < ihi) {
-                    const uint32_t mid = ilo + ((ihi - ilo) >> 1);
-                    uint32_t c = 0;
-#pragma unroll
-                    for (int i = 0; i < E; i++)
-                        c += (x[i] == v && warm_idbase[i >> 2] + (uint32_t)((i & 3) * 32 + lane) <= mid) ? 1u : 0u;
-                    c = __reduce_add_sync(0xffffffffu, c);
-                    if (c >= need) ihi = mid; else ilo = mid + 1;
-                }
-                tmax = ilo;
-            }
+            // Tied k-th score (typically the clamp value): the smallest ids win.  The ids of the parked rows ascend with
+            // the slot order p = i*32 + lane (warps own ascending row ranges), so the tie rule is a running count in the
+            // compaction pass itself -- no second bisection.
+            const bool tied = c_le > kk;   // warp-uniform
+            const uint32_t need = kk - c_lt;  // ties to keep
             // compact the kk survivors into this warp's staging area
             uint32_t ns = 0;
+            const uint32_t lt_mask = (1u << lane) - 1u;
+            if (!tied) {
 #pragma unroll
-            for (int i = 0; i < E; i++) {
-                const uint32_t id = warm_idbase[i >> 2] + (uint32_t)((i & 3) * 32 + lane);
-                const bool pass = x[i] < v || (x[i] == v && id <= tmax);
-                const unsigned msk = __ballot_sync(0xffffffffu, pass);
-                if (pass) sts64(staging_w + (ns + __popc(msk & ((1u << lane) - 1))) * 8u, make_key(x[i] | 0x80000000u, id));
-                ns += __popc(msk);
+                for (int i = 0; i < E; i++) {
+                    const bool pass = x[i] <= v;
+                    const unsigned msk = __ballot_sync(0xffffffffu, pass);
+                    if (pass)
+                        sts64(staging_w + (ns + __popc(msk & lt_mask)) * 8u,
+                              make_key(x[i] | 0x80000000u, warm_idbase[i >> 2] + (uint32_t)((i & 3) * 32 + lane)));
+                    ns += __popc(msk);
+                }
+            } else {
+                uint32_t ties_seen = 0;
+#pragma unroll
+                for (int i = 0; i < E; i++) {
+                    const bool eq = x[i] == v;
+                    const unsigned meq = __ballot_sync(0xffffffffu, eq);
+                    const bool pass = x[i] < v || (eq && ties_seen + __popc(meq & lt_mask) < need);
+                    ties_seen += __popc(meq);
+                    const unsigned msk = __ballot_sync(0xffffffffu, pass);
+                    if (pass)
+                        sts64(staging_w + (ns + __popc(msk & lt_mask)) * 8u,
+                              make_key(x[i] | 0x80000000u, warm_idbase[i >> 2] + (uint32_t)((i & 3) * 32 + lane)));
+                    ns += __popc(msk);
+                }
             }
             if (STATS) st_candB += ns;
             __syncwarp();
@@ -698,14 +800,11 @@ adc_scan_topk_kernel(const uint32_t* __restrict__ codesT,  // [granules][G][64]
     asm volatile("bar.sync 1, %0;" ::"r"(C::WARPS * 32) : "memory");
     if (STATS) t_b2 = now();
     // ---- phase C: stream the rest against the thresholds ----
-    for (; st < n_st; st++) {
-        next_stage();
-        refresh_tau();
-#pragma unroll 4
-        for (int bb = 0; bb < C::STAGE_BLOCKS; bb++, Bg++) block_body(Bg, std::false_type{});
-    }
+    for (; st < n_st; st++) run_stage(std::false_type{}, true);
     refresh_tau();
-    for (int d = 0; d < G - 1; d++, Bg++) block_body(Bg, std::false_type{});  // drain the lane-group pipeline
+    // drain the lane-group pipeline (grouped: whole groups; the surplus blocks lie past the stream and are rejected by row)
+    if constexpr (VAR & 2) run_blocks((G - 1 + 3) & ~3, std::false_type{});
+    else for (int d = 0; d < G - 1; d++, Bg++) block_body(Bg, std::false_type{});
 
     // ---- flush what is still staged, then emit the CTA's sorted lists ----
     flush_lanes(__ballot_sync(0xffffffffu, last_group && cnt > 0), true);
@@ -1109,24 +1208,24 @@ void scan_plan(int sm_count, long long qgroups, long long n_granules, ScanPlan* 
     for (int v : next_slice) plan->slices = std::max(plan->slices, v);
 }
 
-template <int G, int WARPS_>
+template <int G, int WARPS_, int VAR = 0>
 static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
                        int n_full, int n_tail, const int4* tail_desc, int k, float clamp, uint32_t id_base,
                        unsigned long long* out_keys, float* warm_scratch) {
-    using C = ScanCfg<G, WARPS_>;
+    using C = ScanCfg<G, WARPS_, VAR>;
     // the opt-in is per device (a process may hold contexts on several GPUs): set it on every launch, it is a cheap host call
-    B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, false, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const long long n_gran = (n_rows + 63) / 64;
     const unsigned grid = (unsigned)(n_full + n_tail);
     int soft = C::SOFT;
     if (const char* e = getenv("B200NN_SOFT")) soft = std::max(1, std::min(C::SB - 4, atoi(e)));
     if (getenv("B200NN_SCAN_STATS")) {  // development aid: counters of the candidate path, printed per launch
-        B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        B2_CUDA(cudaFuncSetAttribute(adc_scan_topk_kernel<G, WARPS_, true, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         unsigned long long* d_stats = nullptr;
         unsigned long long hs[16];
         B2_CUDA(cudaMalloc(&d_stats, sizeof(hs)));
         B2_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(hs), ctx->stream));
-        adc_scan_topk_kernel<G, WARPS_, true><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
+        adc_scan_topk_kernel<G, WARPS_, true, VAR><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
             codesT, lut_scan, n_rows, n_gran, n_full, tail_desc, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft,
             d_stats, ctx->d_err);
         B2_CUDA(cudaMemcpyAsync(hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1141,7 +1240,7 @@ static int scan_launch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, 
         ctx->launches++;
         return 0;
     }
-    adc_scan_topk_kernel<G, WARPS_, false><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
+    adc_scan_topk_kernel<G, WARPS_, false, VAR><<<grid, C::WARPS * 32, C::SMEM_BYTES, ctx->stream>>>(
         codesT, lut_scan, n_rows, n_gran, n_full, tail_desc, k, clamp, id_base, out_keys, qgroups * C::QW, warm_scratch, soft,
         nullptr, ctx->d_err);
     ctx->launches++;
@@ -1158,8 +1257,27 @@ template <int G>
 static int scan_dispatch(Ctx* ctx, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,
                          int n_full, int n_tail, const int4* tail_desc, int k, float clamp, uint32_t id_base,
                          unsigned long long* out_keys, float* warm_scratch) {
-    return scan_launch<G, 16>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, n_tail, tail_desc, k, clamp, id_base, out_keys,
-                              warm_scratch);
+    // kernel variant: bit 0 = two-slot ring (G = 8 only), bit 1 = grouped threshold check; B200NN_SCAN_VAR overrides (tuning)
+    int var = (G == 8) ? 3 : 2;
+    if (const char* e = getenv("B200NN_SCAN_VAR")) var = atoi(e);
+    if (G != 8) var &= 2;
+#define B2_SCAN_VAR(V_)                                                                                                  \
+    case V_:                                                                                                             \
+        return scan_launch<G, 16, V_>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, n_tail, tail_desc, k, clamp, id_base, \
+                                      out_keys, warm_scratch);
+    switch (var) {
+        B2_SCAN_VAR(2)
+        default: break;
+    }
+    if constexpr (G == 8) {
+        switch (var) {
+            B2_SCAN_VAR(1) B2_SCAN_VAR(3)
+            default: break;
+        }
+    }
+#undef B2_SCAN_VAR
+    return scan_launch<G, 16, 0>(ctx, codesT, lut_scan, n_rows, qgroups, n_full, n_tail, tail_desc, k, clamp, id_base, out_keys,
+                                 warm_scratch);
 }
 
 int launch_adc_scan_topk(Ctx* ctx, int M, const uint32_t* codesT, const float* lut_scan, long long n_rows, long long qgroups,

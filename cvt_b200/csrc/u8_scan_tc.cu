@@ -68,8 +68,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Layout: slot-major, slot j of query t at L_addr + (j * 128) * 8 with L_addr already offset by t: the threads of a warp
 // walk the same slot of 32 different lists together, which is conflict-free for any k.
 constexpr uint32_t TC_SLOT_STRIDE = 128u * 8u;
-__device__ __forceinline__ void list_replace_max(uint32_t L_addr, unsigned long long key, int k, unsigned long long& tkey, int& tpos) {
-    sts64(L_addr + (uint32_t)tpos * TC_SLOT_STRIDE, key);
+// `fill` = occupied slots: while the list is still filling, a key just takes the next free slot (no rescan; tkey stays
+// KEY_MAX, so everything is still accepted); the maximum is looked up once when the k-th slot is taken and after every
+// replacement from then on.
+__device__ __forceinline__ void list_replace_max(uint32_t L_addr, unsigned long long key, int k, unsigned long long& tkey, int& tpos, int& fill) {
+    if (fill < k) {
+        sts64(L_addr + (uint32_t)fill * TC_SLOT_STRIDE, key);
+        if (++fill < k) return;
+    } else {
+        sts64(L_addr + (uint32_t)tpos * TC_SLOT_STRIDE, key);
+    }
     unsigned long long mx = 0;
     int mp = 0;
 #pragma unroll 4
@@ -81,13 +89,17 @@ __device__ __forceinline__ void list_replace_max(uint32_t L_addr, unsigned long 
     tpos = mp;
 }
 
+constexpr int TC_BOUND_LISTS = 32;          // lists per query whose minima are shared (shared-bound mode)
+constexpr int TC_INF = 0x7f7f7f7f;          // "no distance yet" (memset pattern; above every real distance)
+
 template <int TC_GROUPS>
-__global__ void __launch_bounds__(TC_GROUPS * 128 + 32, 1)
+__global__ void __launch_bounds__(TC_GROUPS * 128 + 64, 1)
 u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32][8][16] canonical B tiles
                   const int* __restrict__ xmeta,             // [tiles][2][256]: |x|^2 (padded rows: large), label rank
                   long long n, long long tile0, long long n_tiles,  // rows indexed; this launch scans tiles [tile0, tile0 + n_tiles)
                   int D, const unsigned char* __restrict__ queries, long long nq, int n_slices, int k,
                   const int* __restrict__ init_thr, int init_stride,  // optional: an upper bound on each query's k-th best distance
+                  int* __restrict__ gmin,  // optional [nq][32], preset to TC_INF: shared-bound mode (see the bound warp below)
                   int NS,                                              // B-tile ring stages (2..4, as many as shared memory allows)
                   unsigned long long* __restrict__ out_keys /*[slice * groups + group][nq][k]*/) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -101,11 +113,13 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
     const int MS = NS + 2;
     const uint32_t sXN = sB + (uint32_t)NS * B_BYTES;  // MS stages x (256 norms + 256 ranks)
     const uint32_t sList = sXN + (uint32_t)MS * TC_META_BYTES;       // [groups][128][k] keys
-    constexpr int TC_THREADS = TC_GROUPS * 128 + 32, TC_PRODUCER_WARP = TC_GROUPS * 4;
+    constexpr int TC_THREADS = TC_GROUPS * 128 + 64, TC_PRODUCER_WARP = TC_GROUPS * 4, TC_BOUND_WARP = TC_GROUPS * 4 + 1;
     const uint32_t sScratch = sList + (uint32_t)(TC_GROUPS * TC_M * k) * 8u;   // [warps][32 columns][32 lanes] words
     const uint32_t sQn = sScratch + TC_GROUPS * 4 * 32 * 32 * 4;             // [128] |q|^2
     const uint32_t bars = sQn + TC_M * 4;
     const uint32_t b_full = bars, b_empty = bars + 32, acc_full = bars + 64, acc_empty = bars + 80, tmem_slot = bars + 96;
+    const uint32_t sDone = bars + 112;   // epilogue warps that have finished their tiles
+    const uint32_t sTp = bars + 128;     // [128] shared bound on each query's k-th best DISTANCE (TC_INF: none yet)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long q0 = (long long)blockIdx.x * TC_M;
     const int slice = blockIdx.y;
@@ -146,6 +160,8 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
                          : "memory");
         }
         asm volatile("st.shared.s32 [%0], %1;" ::"r"(sQn + (uint32_t)tid * 4u), "r"(qn) : "memory");
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(sTp + (uint32_t)tid * 4u), "r"(TC_INF) : "memory");
+        if (tid == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(sDone), "r"(0) : "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -187,6 +203,58 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
                 }
             }
         }
+    } else if (warp == TC_BOUND_WARP) {
+        // ===== shared bound (one-pass mode) =====
+        // Every (slice, group) list of a query covers its own rows, so the k-th smallest of the lists' MINIMA is the
+        // distance of at least k distinct rows: an upper bound on the query's final k-th best that is almost as tight as a
+        // merge of the lists would give (the k best rows mostly sit in different lists), available after the first few
+        // tiles and without any pass structure or barrier.  The first TC_BOUND_LISTS lists of a query publish their
+        // minimum (a plain store whenever it improves); this warp keeps re-reading them (thread = query, 4 rounds),
+        // selects the k-th smallest by bisection in registers and posts it in shared memory, where the epilogue
+        // threads pick it up once per tile.  Nothing ever waits on it: a stale value is merely a weaker bound.
+        if (gmin != nullptr) {
+            unsigned sleep_ns = 0;  // the bound moves fast at first and hardly at all later: back off
+            for (int r = 0;; r = (r + 1) & (TC_M / 32 - 1)) {
+                int done = 0;
+                if (lane == 0) asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(done) : "r"(sDone));
+                done = __shfl_sync(0xffffffffu, done, 0);
+                if (done >= TC_GROUPS * 4) break;
+                {
+                    const int q = r * 32 + lane;
+                    int v[TC_BOUND_LISTS];
+                    const int4* src = reinterpret_cast<const int4*>(gmin + (q0 + q) * TC_BOUND_LISTS);
+#pragma unroll
+                    for (int i = 0; i < TC_BOUND_LISTS / 4; i++) {
+                        int4 t = make_int4(TC_INF, TC_INF, TC_INF, TC_INF);
+                        if (q0 + q < nq) t = __ldcg(src + i);
+                        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+                    }
+                    int lo = TC_INF, hi = -1, fin = 0;
+#pragma unroll
+                    for (int i = 0; i < TC_BOUND_LISTS; i++)
+                        if (v[i] < TC_INF) { fin++; lo = min(lo, v[i]); hi = max(hi, v[i]); }
+                    int res = TC_INF;
+                    if (fin >= k) {
+                        while (lo < hi) {  // smallest value with at least k minima at or below it
+                            const int mid = lo + ((hi - lo) >> 1);
+                            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+                            for (int i = 0; i < TC_BOUND_LISTS; i += 4) {
+                                c0 += (v[i] <= mid) ? 1 : 0; c1 += (v[i + 1] <= mid) ? 1 : 0;
+                                c2 += (v[i + 2] <= mid) ? 1 : 0; c3 += (v[i + 3] <= mid) ? 1 : 0;
+                            }
+                            if ((c0 + c1) + (c2 + c3) >= k) hi = mid; else lo = mid + 1;
+                        }
+                        res = lo;
+                    }
+                    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(sTp + (uint32_t)q * 4u), "r"(res) : "memory");
+                }
+                if (r == TC_M / 32 - 1) {
+                    if (sleep_ns) __nanosleep(sleep_ns);
+                    sleep_ns = min(4000u, sleep_ns * 2u + 250u);
+                }
+            }
+        }
     } else {
         // ===== epilogue group g = warp / 4: thread owns query ql = tid % 128 (TMEM lane ql), columns [128 g, 128 g + 128) of every tile =====
         const int grp = warp >> 2, ql = tid & (TC_M - 1);
@@ -200,7 +268,12 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
         int tp = 0x7fffffff;
         if (init_thr != nullptr && qvalid) tp = __ldg(init_thr + (q0 + ql) * init_stride) - qn;
         unsigned long long tkey = KEY_MAX;
-        int tpos = 0;
+        int tpos = 0, fill = 0;
+        // shared-bound mode: this list publishes its minimum if it is one of the query's first TC_BOUND_LISTS lists
+        const int list_id = slice * TC_GROUPS + grp;
+        const bool publish = gmin != nullptr && qvalid && list_id < TC_BOUND_LISTS;
+        int* const gslot = gmin + (q0 + ql) * TC_BOUND_LISTS + list_id;
+        int lmin = TC_INF;
         auto tld32 = [&](uint32_t (&r)[32], uint32_t taddr) {
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -246,7 +319,11 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rk) : "r"(meta_s + (uint32_t)(TC_N + c0 + i) * 4u));
                         const unsigned long long key = make_key(s32_orderable(dp + qn), rk);
                         if (key < tkey) {
-                            list_replace_max(myList, key, k, tkey, tpos);
+                            list_replace_max(myList, key, k, tkey, tpos, fill);
+                            if (publish && dp + qn < lmin) {
+                                lmin = dp + qn;
+                                asm volatile("st.global.cg.s32 [%0], %1;" ::"l"(gslot), "r"(lmin) : "memory");
+                            }
                             if (tkey != KEY_MAX) tp = min(tp, s32_from_orderable((uint32_t)(tkey >> 32)) - qn);  // list full: k-th distance
                         }
                     }
@@ -259,6 +336,11 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
             mbar_wait(acc_full + 8 * s, (uint32_t)use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long row_base = (t_lo + t) * TC_N;
+            if (gmin != nullptr) {  // the bound posted by the bound warp (a DISTANCE; tp is relative to |q|^2)
+                int sh;
+                asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(sh) : "r"(sTp + (uint32_t)ql * 4u));
+                tp = min(tp, sh - qn);
+            }
             const uint32_t meta_s = sXN + (uint32_t)(t % MS) * TC_META_BYTES;
             const int cg = grp * (TC_N / TC_GROUPS);
             const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * TC_N + cg);
@@ -277,6 +359,8 @@ u8_scan_tc_kernel(const unsigned char* __restrict__ xcan,   // [tiles][D/16][32]
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * s);
         }
+        __syncwarp();
+        if (lane == 0) asm volatile("red.shared.add.s32 [%0], 1;" ::"r"(sDone) : "memory");
         if (qvalid) {  // emit the list ascending: rank of an entry = how many entries order before it
             unsigned long long* out = out_keys + ((long long)(slice * TC_GROUPS + grp) * nq + q0 + ql) * k;
             for (int j = 0; j < k; j++) {
@@ -329,12 +413,13 @@ __global__ void u8_rows_to_canonical_kernel(const unsigned char* __restrict__ ro
 
 static size_t tc_smem_bytes(int D, int k, int groups, int stages) {
     return (size_t)TC_M * D + (size_t)stages * TC_N * D + (size_t)(stages + 2) * TC_META_BYTES +
-           (size_t)groups * (TC_M * (size_t)k * 8 + 4 * 32 * 32 * 4) + TC_M * 4 + 256;
+           (size_t)groups * (TC_M * (size_t)k * 8 + 4 * 32 * 32 * 4) + TC_M * 4 + 128 + TC_M * 4 + 128;
 }
 // Two epilogue groups when their lists and scratch fit beside the operand tiles, else one.  (Four groups -- 16 epilogue warps,
 // 64 accumulator columns each -- were measured: the bulk pass of cfg2 went from 233 to 223 us only, because the drain is
 // bound by the TMEM read port, 64 B/clk per SM = 2048 clk for the 128 KB of int32 accumulators of a tile, not by issue or
 // latency; the extra lists made the merges dearer than that gain.)
+int u8_scan_tc_bound_lists() { return TC_BOUND_LISTS; }
 int u8_scan_tc_lists_per_slice(int D, int k) { return tc_smem_bytes(D, k, 2, 2) <= (size_t)TC_MAX_SMEM ? 2 : 1; }
 
 bool u8_scan_tc_supported(int D, int k) {
@@ -360,7 +445,7 @@ int u8_scan_tc_slices(int sm_count, long long nq, long long n_tiles, int min_til
 }
 
 int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, long long tile0, long long n_tiles, int D,
-                      const unsigned char* queries, long long nq, int n_slices, int k, const int* init_thr, int init_stride,
+                      const unsigned char* queries, long long nq, int n_slices, int k, const int* init_thr, int init_stride, int* gmin,
                       unsigned long long* out_keys) {
     if (nq <= 0 || n_tiles <= 0) return 0;
     if (!u8_scan_tc_supported(D, k)) B2_FAIL(-4, "u8 tensor-core scan: needs D % 32 == 0, D <= 256 and k lists that fit shared memory");
@@ -371,10 +456,10 @@ int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, lon
     dim3 grid((unsigned)((nq + TC_M - 1) / TC_M), (unsigned)n_slices);
     if (groups == 2) {
         B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        u8_scan_tc_kernel<2><<<grid, 2 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, tile0, n_tiles, D, queries, nq, n_slices, k, init_thr, init_stride, stages, out_keys);
+        u8_scan_tc_kernel<2><<<grid, 2 * 128 + 64, smem, ctx->stream>>>(xcan, xmeta, n, tile0, n_tiles, D, queries, nq, n_slices, k, init_thr, init_stride, gmin, stages, out_keys);
     } else {
         B2_CUDA(cudaFuncSetAttribute(u8_scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        u8_scan_tc_kernel<1><<<grid, 1 * 128 + 32, smem, ctx->stream>>>(xcan, xmeta, n, tile0, n_tiles, D, queries, nq, n_slices, k, init_thr, init_stride, stages, out_keys);
+        u8_scan_tc_kernel<1><<<grid, 1 * 128 + 64, smem, ctx->stream>>>(xcan, xmeta, n, tile0, n_tiles, D, queries, nq, n_slices, k, init_thr, init_stride, gmin, stages, out_keys);
     }
     ctx->launches++;
     B2_CUDA(cudaGetLastError());

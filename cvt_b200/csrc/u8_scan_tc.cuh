@@ -16,8 +16,12 @@ int u8_scan_tc_lists_per_slice(int D, int k);
 // init_thr (may be NULL): init_thr[q * init_stride] = an upper bound on query q's k-th best distance, e.g. the k-th
 // best over a prefix of the rows -- rows beyond it are dropped (ties kept), so lists may come back shorter than k.
 // The launch scans tiles [tile0, tile0 + n_tiles) of the index (n = rows indexed, for the validity of the last tile).
+// gmin (may be NULL): [nq][u8_scan_tc_bound_lists()] ints preset to 0x7f7f7f7f -- one-pass shared-bound mode: the first
+// lists of every query publish their minimum there and a bound warp per CTA turns them into a running upper bound on the
+// k-th best distance (k-th smallest of the minima); needs k <= min(bound lists, n_slices * lists per slice).
+int u8_scan_tc_bound_lists();
 int launch_u8_scan_tc(Ctx* ctx, const unsigned char* xcan, const int* xmeta, long long n, long long tile0, long long n_tiles, int D,
-                      const unsigned char* queries, long long nq, int n_slices, int k, const int* init_thr, int init_stride,
+                      const unsigned char* queries, long long nq, int n_slices, int k, const int* init_thr, int init_stride, int* gmin,
                       unsigned long long* out_keys);
 
 }  // namespace b200nn

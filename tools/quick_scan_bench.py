@@ -31,3 +31,9 @@ for it in range(5):
 kth = od[:, k-1].cpu().numpy()
 print("k-th score: median %.4f  frac<1.0: %.4f" % (np.median(kth), (kth < 1.0).mean()))
 print("launches", ctx.launch_count())
+import hashlib
+print("ids sha1", hashlib.sha1(oi.cpu().numpy().tobytes()).hexdigest()[:16], "scores sha1", hashlib.sha1(od.cpu().numpy().tobytes()).hexdigest()[:16])
+if os.environ.get("QUICK_STATS"):
+    os.environ["B200NN_SCAN_STATS"] = "1"
+    idx.search_dev(qd.data_ptr(), B, k, 1, od.data_ptr(), oi.data_ptr())
+    ctx.synchronize()
