@@ -245,7 +245,7 @@ static double layout_cost(int world, int R, long long n_rows, long long batch, i
     auto segment = [&](double r) { return 30e-6 + qw * 1.5 * k * log(std::max(r, 4096.0) / 2048.0) * 0.015e-6; };
     const long long waves = groups / sm, rem = groups % sm;
     const double t_warm = waves * segment(rows) + (rem ? 1.5 * segment((double)rem * rows / sm) : 0.0);
-    const double t_scan = bq * rows * M / 6.0e12, t_lut = bq * 0.02e-6;
+    const double t_scan = bq * rows * M / 6.4e12, t_lut = bq * 0.012e-6;
     const double gathered = (double)world * bq * k * 8;
     const double t_x = world == 1 ? 0.0 : 40e-6 + gathered / 300e9 + (R > 1 ? gathered / 1.0e12 : 0.0);
     return t_scan + t_warm + t_lut + t_x;

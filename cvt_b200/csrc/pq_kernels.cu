@@ -876,74 +876,137 @@ __global__ void ivf_scan_kernel(const float* __restrict__ lut,            // [nq
 // IVFOPQ.cpp:369) and get_sort_results breaks ties by id, so when fewer than k probed rows score
 // below the clamp the tail is the smallest row ids at exactly `clamp` (probed or not).
 // =============================================================================================
+constexpr int IVF_PG = 4;  // probes whose LUTs are built together (shared memory: IVF_PG x M x ksub floats)
 template <int DS>
 __global__ void __launch_bounds__(256)
 ivf_search_topk_kernel(const float* __restrict__ q_rot, long long nq, int D, const int* __restrict__ probes, int nprobe,
                        const float* __restrict__ coarse, const float* __restrict__ cb, int M, int ksub,
                        const long long* __restrict__ list_off, const unsigned char* __restrict__ codes_sorted,
-                       const int* __restrict__ row_sorted, long long n_rows, int k, float clamp, uint32_t id_base,
+                       const int* __restrict__ row_sorted, long long n_rows, int k, float clamp, uint32_t id_base, int n_pg /* <= IVF_PG */,
                        unsigned long long* __restrict__ out_keys) {
-    constexpr int SBW = 64;
+    // Selection: the probed lists are short (1 M rows over 8192 lists: ~120 rows each), so a query sees a few hundred
+    // candidates in all.  They are appended to ONE buffer per CTA (warp-aggregated slot counter) and the buffer is sorted
+    // by a bitonic network when it is about to overflow and once at the end -- no per-warp staging, no lock, no
+    // serialised list merges (those were ~12 lock-ordered merges per query, the bulk of the kernel's time).
+    constexpr int BUF = 1024;
     extern __shared__ __align__(16) unsigned char dsm[];
-    float* s_lut = reinterpret_cast<float*>(dsm);                 // [M*ksub]
-    float* s_res = s_lut + M * ksub;                              // [D]
-    __shared__ __align__(16) unsigned long long s_list[KP];
-    __shared__ __align__(16) unsigned long long s_stage[8][SBW];
-    __shared__ unsigned long long s_tau;
-    __shared__ int s_lock;
+    float* s_lut = reinterpret_cast<float*>(dsm);                 // [n_pg][M*ksub]
+    float* s_res = s_lut + n_pg * M * ksub;                       // [n_pg][D]
+    __shared__ __align__(16) unsigned long long s_list[BUF];      // [0, s_cnt): the best so far (first k sorted after a trim) + new candidates
+    __shared__ unsigned long long s_tau;                           // k-th best record after the last trim (KEY_MAX: fewer than k yet)
+    __shared__ int s_cnt;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long q = blockIdx.x;
-    for (int i = threadIdx.x; i < KP; i += blockDim.x) s_list[i] = KEY_MAX;
-    if (threadIdx.x == 0) { s_tau = KEY_MAX; s_lock = 0; }
-    const uint32_t L = smem_u32(s_list), ST = smem_u32(&s_stage[w][0]);
-    volatile unsigned long long* tau_p = &s_tau;
-    int cnt = 0;
-    auto flush_all = [&]() {
-        for (int off = 0; off < cnt; off += 32) warp_flush(L, &s_lock, tau_p, ST + off * 8, min(32, cnt - off), k);
-        cnt = 0;
-    };
-    const uint32_t clamp_ord = f32_orderable(clamp);
-    for (int p = 0; p < nprobe; p++) {
-        const int vw = probes[q * nprobe + p];
-        __syncthreads();  // previous LUT fully consumed; lists initialised
-        for (int j = threadIdx.x; j < D; j += blockDim.x) s_res[j] = __fsub_rn(q_rot[q * D + j], coarse[(long long)vw * D + j]);
+    if (threadIdx.x == 0) { s_tau = KEY_MAX; s_cnt = 0; }
+    // sort s_list[0, s_cnt) ascending (padded with KEY_MAX to a power of two >= 256), keep the best k
+    auto sort_and_trim = [&]() {
         __syncthreads();
-        for (int e = threadIdx.x; e < M * ksub; e += blockDim.x) {
-            const int m = e / ksub, j = e - m * ksub;
-            const float* c = cb + ((long long)m * ksub + j) * DS;
-            float acc = 0.0f;
-#pragma unroll
-            for (int t = 0; t < DS; t++) {
-                const float d = __fsub_rn(s_res[m * DS + t], __ldg(c + t));
-                acc = __fadd_rn(acc, __fmul_rn(d, d));
+        const int have = s_cnt;
+        int n2 = 256;
+        while (n2 < have) n2 <<= 1;
+        for (int i = have + threadIdx.x; i < n2; i += blockDim.x) s_list[i] = KEY_MAX;
+        __syncthreads();
+        for (int size = 2; size <= n2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                    const int i = 2 * t - (t & (stride - 1)), j = i + stride;  // i has bit `stride` clear
+                    const unsigned long long a = s_list[i], b2 = s_list[j];
+                    const bool up = (i & size) == 0;
+                    if ((a > b2) == up) { s_list[i] = b2; s_list[j] = a; }
+                }
+                __syncthreads();
             }
-            s_lut[e] = acc;
+        if (threadIdx.x == 0) {
+            const int keep = min(have, k);
+            s_cnt = keep;
+            s_tau = keep >= k ? s_list[k - 1] : KEY_MAX;
         }
         __syncthreads();
-        const long long lo = list_off[vw], hi = list_off[vw + 1];
-        for (long long r0 = lo + (long long)w * 32; r0 < hi; r0 += 8 * 32) {
-            const long long r = r0 + lane;
-            bool pass = false;
-            unsigned long long key = 0;
-            if (r < hi) {
-                const unsigned char* c = codes_sorted + r * M;
-                float score = 0.0f;
-                for (int m = 0; m < M; m++) score = __fadd_rn(score, s_lut[m * ksub + c[m]]);
-                if (score < clamp) {  // rows at or above the clamp are indistinguishable from unprobed rows
-                    key = make_key(f32_orderable(score), id_base + (uint32_t)row_sorted[r]);
-                    pass = key < *tau_p;
+    };
+    const uint32_t clamp_ord = f32_orderable(clamp);
+    // The LUTs of up to IVF_PG probes are built in ONE pass over the codebook (a codeword row is loaded once, with 16-byte
+    // loads, and meets every probe's residual): a third of the L2 traffic and of the CTA barriers of a LUT per probe.
+    const int LUTN = M * ksub;
+    for (int p0 = 0; p0 < nprobe; p0 += n_pg) {
+        const int pg = min(n_pg, nprobe - p0);
+        __syncthreads();  // previous LUTs fully consumed; lists initialised
+        for (int i = threadIdx.x; i < pg * D; i += blockDim.x) {
+            const int pp = i / D, j = i - pp * D;
+            const int vw = probes[q * nprobe + p0 + pp];
+            s_res[pp * D + j] = __fsub_rn(q_rot[q * D + j], coarse[(long long)vw * D + j]);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < LUTN; e += blockDim.x) {
+            const int m = e / ksub;
+            const float* c = cb + (long long)e * DS;
+            float cv[DS];
+            if (DS % 4 == 0) {
+#pragma unroll
+                for (int t = 0; t < DS; t += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(c + t));
+                    cv[t] = v.x; cv[t + 1] = v.y; cv[t + 2] = v.z; cv[t + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < DS; t++) cv[t] = __ldg(c + t);
+            }
+#pragma unroll
+            for (int pp = 0; pp < IVF_PG; pp++) {
+                if (pp < pg) {
+                    const float* r = s_res + pp * D + m * DS;
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int t = 0; t < DS; t++) {
+                        const float d = __fsub_rn(r[t], cv[t]);
+                        acc = __fadd_rn(acc, __fmul_rn(d, d));
+                    }
+                    s_lut[pp * LUTN + e] = acc;
                 }
             }
-            const unsigned msk = __ballot_sync(0xffffffffu, pass);
-            if (msk) {
-                if (pass) sts64(ST + (uint32_t)(cnt + __popc(msk & ((1u << lane) - 1))) * 8u, key);
-                cnt += __popc(msk);
-                __syncwarp();
-                if (cnt > SBW - 32) flush_all();
+        }
+        __syncthreads();
+        for (int pp = 0; pp < pg; pp++) {
+            const int vw = probes[q * nprobe + p0 + pp];
+            const float* lut = s_lut + pp * LUTN;
+            const long long lo = list_off[vw], hi = list_off[vw + 1];
+            for (long long r0 = lo; r0 < hi; r0 += blockDim.x) {  // CTA-uniform passes of 256 rows
+                if (s_cnt > BUF - (int)blockDim.x) sort_and_trim();  // CTA-uniform: s_cnt only changes between barriers
+                const unsigned long long tau = s_tau;
+                const long long r = r0 + threadIdx.x;
+                bool pass = false;
+                unsigned long long key = 0;
+                if (r < hi) {
+                    const unsigned char* c = codes_sorted + r * M;
+                    float score = 0.0f;
+                    if ((M & 15) == 0) {  // 16 code bytes per load
+                        for (int m0 = 0; m0 < M; m0 += 16) {
+                            const uint4 cw = __ldg(reinterpret_cast<const uint4*>(c + m0));
+                            const uint32_t wd[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                            for (int u = 0; u < 16; u++)
+                                score = __fadd_rn(score, lut[(m0 + u) * ksub + ((wd[u >> 2] >> (8 * (u & 3))) & 0xFFu)]);
+                        }
+                    } else {
+                        for (int m = 0; m < M; m++) score = __fadd_rn(score, lut[m * ksub + c[m]]);
+                    }
+                    if (score < clamp) {  // rows at or above the clamp are indistinguishable from unprobed rows
+                        key = make_key(f32_orderable(score), id_base + (uint32_t)row_sorted[r]);
+                        pass = key < tau;
+                    }
+                }
+                const unsigned msk = __ballot_sync(0xffffffffu, pass);
+                if (msk) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_cnt, __popc(msk));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (pass) s_list[base + __popc(msk & ((1u << lane) - 1))] = key;
+                }
+                __syncthreads();  // s_cnt settled before the next pass reads it
             }
         }
     }
-    flush_all();
+    sort_and_trim();
+    for (int i = s_cnt + threadIdx.x; i < k; i += blockDim.x) s_list[i] = KEY_MAX;  // unfilled slots (the sort's padding may end below k)
     __syncthreads();
     // Fewer than k probed rows scored below the clamp: the tail is (clamp, smallest ids not already in the list), IVFOPQ.cpp:369 +
     // common.h:25-37.  The list holds real < k records, so among the ids [0, 2k) at least k are absent: thread t < 2k tests id t
@@ -1344,14 +1407,16 @@ int launch_ivf_search_topk(Ctx* ctx, const float* q_rot, long long nq, int D, co
     if (nq <= 0) return 0;
     if (k < 1 || k > KP) B2_FAIL(-4, "IVF search supports 1 <= k <= 128");
     const int ds = D / M;
-    const size_t smem = ((size_t)M * ksub + D) * sizeof(float);
+    const size_t per_probe = ((size_t)M * ksub + D) * sizeof(float);
+    const int n_pg = (int)std::max<size_t>(1, std::min<size_t>(std::min(IVF_PG, nprobe), (160u << 10) / per_probe));
+    const size_t smem = (size_t)n_pg * per_probe;
 #define B2_IVF(DS_)                                                                                                          \
     case DS_:                                                                                                                \
         if (smem > 40 * 1024)                                                                                                \
             B2_CUDA(cudaFuncSetAttribute(ivf_search_topk_kernel<DS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         ivf_search_topk_kernel<DS_><<<(unsigned)nq, 256, smem, ctx->stream>>>(q_rot, nq, D, probes, nprobe, coarse, cb, M, ksub, \
                                                                              list_off, codes_sorted, row_sorted, n_rows, k, clamp, \
-                                                                             id_base, out_keys);                              \
+                                                                             id_base, n_pg, out_keys);                        \
         break;
     switch (ds) {
         B2_IVF(1) B2_IVF(2) B2_IVF(4) B2_IVF(8) B2_IVF(16) B2_IVF(32)
