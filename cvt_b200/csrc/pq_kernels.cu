@@ -876,6 +876,34 @@ __global__ void ivf_scan_kernel(const float* __restrict__ lut,            // [nq
 // IVFOPQ.cpp:369) and get_sort_results breaks ties by id, so when fewer than k probed rows score
 // below the clamp the tail is the smallest row ids at exactly `clamp` (probed or not).
 // =============================================================================================
+// CTA-wide selection buffer shared by the list/matrix selection kernels: keys are appended to s_list[0, *s_cnt) (warp-
+// aggregated counter) and this sorts them ascending with a bitonic network (padded with KEY_MAX to a power of two >= 256),
+// keeps the best k and publishes the k-th best as the new threshold.  Must be called by every thread of the CTA.
+__device__ __forceinline__ void cta_sort_trim(unsigned long long* s_list, int* s_cnt, unsigned long long* s_tau, int k) {
+    __syncthreads();
+    const int have = *s_cnt;
+    int n2 = 256;
+    while (n2 < have) n2 <<= 1;
+    for (int i = have + threadIdx.x; i < n2; i += blockDim.x) s_list[i] = KEY_MAX;
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                const int i = 2 * t - (t & (stride - 1)), j = i + stride;  // i has bit `stride` clear
+                const unsigned long long a = s_list[i], b = s_list[j];
+                const bool up = (i & size) == 0;
+                if ((a > b) == up) { s_list[i] = b; s_list[j] = a; }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        const int keep = min(have, k);
+        *s_cnt = keep;
+        *s_tau = keep >= k ? s_list[k - 1] : KEY_MAX;
+    }
+    __syncthreads();
+}
+
 constexpr int IVF_PG = 4;  // probes whose LUTs are built together (shared memory: IVF_PG x M x ksub floats)
 template <int DS>
 __global__ void __launch_bounds__(256)
@@ -898,31 +926,7 @@ ivf_search_topk_kernel(const float* __restrict__ q_rot, long long nq, int D, con
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long q = blockIdx.x;
     if (threadIdx.x == 0) { s_tau = KEY_MAX; s_cnt = 0; }
-    // sort s_list[0, s_cnt) ascending (padded with KEY_MAX to a power of two >= 256), keep the best k
-    auto sort_and_trim = [&]() {
-        __syncthreads();
-        const int have = s_cnt;
-        int n2 = 256;
-        while (n2 < have) n2 <<= 1;
-        for (int i = have + threadIdx.x; i < n2; i += blockDim.x) s_list[i] = KEY_MAX;
-        __syncthreads();
-        for (int size = 2; size <= n2; size <<= 1)
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
-                    const int i = 2 * t - (t & (stride - 1)), j = i + stride;  // i has bit `stride` clear
-                    const unsigned long long a = s_list[i], b2 = s_list[j];
-                    const bool up = (i & size) == 0;
-                    if ((a > b2) == up) { s_list[i] = b2; s_list[j] = a; }
-                }
-                __syncthreads();
-            }
-        if (threadIdx.x == 0) {
-            const int keep = min(have, k);
-            s_cnt = keep;
-            s_tau = keep >= k ? s_list[k - 1] : KEY_MAX;
-        }
-        __syncthreads();
-    };
+    auto sort_and_trim = [&]() { cta_sort_trim(s_list, &s_cnt, &s_tau, k); };
     const uint32_t clamp_ord = f32_orderable(clamp);
     // The LUTs of up to IVF_PG probes are built in ONE pass over the codebook (a codeword row is loaded once, with 16-byte
     // loads, and meets every probe's residual): a third of the L2 traffic and of the CTA barriers of a LUT per probe.
@@ -1058,41 +1062,54 @@ __global__ void frame_sum_kernel(const float* scores, int n_frames, long long ng
 __global__ void __launch_bounds__(256)
 dense_topk_kernel(const float* __restrict__ values, long long n, long long ld, int k, const uint32_t* __restrict__ id_map,
                   unsigned long long* __restrict__ out_keys) {
-    constexpr int SBW = 64;
-    __shared__ __align__(16) unsigned long long s_list[KP];
-    __shared__ __align__(16) unsigned long long s_stage[8][SBW];
+    // passes of 1024 columns, four coalesced loads in flight per thread; a value meets the threshold's SCORE first and only
+    // a survivor fetches its id; survivors go to the CTA buffer (cta_sort_trim): one sort after the first pass sets the
+    // threshold, after which a pass rarely holds a candidate at all.
+    constexpr int BUF = 2048, PASS = 1024;
+    __shared__ __align__(16) unsigned long long s_list[BUF];
     __shared__ unsigned long long s_tau;
-    __shared__ int s_lock;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __shared__ int s_cnt;
+    const int lane = threadIdx.x & 31;
     const float* v = values + (long long)blockIdx.x * ld;
     const long long c_lo = (n * blockIdx.y) / gridDim.y, c_hi = (n * (blockIdx.y + 1)) / gridDim.y;
-    for (int i = threadIdx.x; i < KP; i += blockDim.x) s_list[i] = KEY_MAX;
-    if (threadIdx.x == 0) { s_tau = KEY_MAX; s_lock = 0; }
+    if (threadIdx.x == 0) { s_tau = KEY_MAX; s_cnt = 0; }
     __syncthreads();
-    const uint32_t L = smem_u32(s_list), ST = smem_u32(&s_stage[w][0]);
-    volatile unsigned long long* tau_p = &s_tau;
-    int cnt = 0;
-    auto flush_all = [&]() {
-        for (int off = 0; off < cnt; off += 32) warp_flush(L, &s_lock, tau_p, ST + off * 8, min(32, cnt - off), k);
-        cnt = 0;
-    };
-    for (long long r0 = c_lo + (long long)w * 32; r0 < c_hi; r0 += 8 * 32) {
-        const long long r = r0 + lane;
-        unsigned long long key = KEY_MAX;
-        if (r < c_hi) key = make_key(f32_orderable(v[r]), id_map ? __ldg(id_map + r) : (uint32_t)r);
-        const bool pass = key < *tau_p;
-        const unsigned msk = __ballot_sync(0xffffffffu, pass);
-        if (msk) {
-            if (pass) sts64(ST + (uint32_t)(cnt + __popc(msk & ((1u << lane) - 1))) * 8u, key);
-            cnt += __popc(msk);
-            __syncwarp();
-            if (cnt > SBW - 32) flush_all();
+    for (long long c0 = c_lo; c0 < c_hi; c0 += PASS) {
+        // CTA-uniform: s_cnt and s_tau only change between barriers
+        if (s_cnt > BUF - PASS || (s_tau == KEY_MAX && s_cnt >= k)) cta_sort_trim(s_list, &s_cnt, &s_tau, k);
+        const unsigned long long tau = s_tau;
+        const uint32_t tau_ord = (uint32_t)(tau >> 32);
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long col = c0 + j * 256 + threadIdx.x;
+            x[j] = col < c_hi ? v[col] : 0.0f;
         }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long long col = c0 + j * 256 + threadIdx.x;
+            bool pass = false;
+            unsigned long long key = 0;
+            if (col < c_hi) {
+                const uint32_t ord = f32_orderable(x[j]);
+                if (ord <= tau_ord) {
+                    key = make_key(ord, id_map ? __ldg(id_map + col) : (uint32_t)col);
+                    pass = key < tau;
+                }
+            }
+            const unsigned msk = __ballot_sync(0xffffffffu, pass);
+            if (msk) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_cnt, __popc(msk));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) s_list[base + __popc(msk & ((1u << lane) - 1))] = key;
+            }
+        }
+        __syncthreads();
     }
-    flush_all();
-    __syncthreads();
+    cta_sort_trim(s_list, &s_cnt, &s_tau, k);
     unsigned long long* out = out_keys + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * k;
-    for (int j = threadIdx.x; j < k; j += blockDim.x) out[j] = s_list[j];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) out[j] = s_list[j];  // slots past the columns scanned hold KEY_MAX (the sort's padding)
 }
 
 __global__ void fill_f32_kernel(float* p, long long n, float v) {
