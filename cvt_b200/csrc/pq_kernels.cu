@@ -1062,10 +1062,11 @@ __global__ void frame_sum_kernel(const float* scores, int n_frames, long long ng
 __global__ void __launch_bounds__(256)
 dense_topk_kernel(const float* __restrict__ values, long long n, long long ld, int k, const uint32_t* __restrict__ id_map,
                   unsigned long long* __restrict__ out_keys) {
-    // passes of 1024 columns, four coalesced loads in flight per thread; a value meets the threshold's SCORE first and only
-    // a survivor fetches its id; survivors go to the CTA buffer (cta_sort_trim): one sort after the first pass sets the
-    // threshold, after which a pass rarely holds a candidate at all.
-    constexpr int BUF = 2048, PASS = 1024;
+    // passes of 2048 columns, eight coalesced loads per thread, the NEXT pass's loads already in flight while this one is
+    // filtered (the matrix comes from DRAM: the kernel is bound by bytes in flight); a value meets the threshold's SCORE first
+    // and only a survivor fetches its id; survivors go to the CTA buffer (cta_sort_trim): one sort after the first pass sets
+    // the threshold, after which a pass rarely holds a candidate at all.
+    constexpr int PER = 8, PASS = PER * 256, BUF = 2 * PASS;
     __shared__ __align__(16) unsigned long long s_list[BUF];
     __shared__ unsigned long long s_tau;
     __shared__ int s_cnt;
@@ -1073,20 +1074,24 @@ dense_topk_kernel(const float* __restrict__ values, long long n, long long ld, i
     const float* v = values + (long long)blockIdx.x * ld;
     const long long c_lo = (n * blockIdx.y) / gridDim.y, c_hi = (n * (blockIdx.y + 1)) / gridDim.y;
     if (threadIdx.x == 0) { s_tau = KEY_MAX; s_cnt = 0; }
+    float x[PER], nx[PER];
+    auto fetch = [&](float (&d)[PER], long long c0) {
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            const long long col = c0 + j * 256 + threadIdx.x;
+            d[j] = col < c_hi ? __ldcs(v + col) : 0.0f;  // read once: streaming
+        }
+    };
+    fetch(x, c_lo);
     __syncthreads();
     for (long long c0 = c_lo; c0 < c_hi; c0 += PASS) {
+        if (c0 + PASS < c_hi) fetch(nx, c0 + PASS);
         // CTA-uniform: s_cnt and s_tau only change between barriers
         if (s_cnt > BUF - PASS || (s_tau == KEY_MAX && s_cnt >= k)) cta_sort_trim(s_list, &s_cnt, &s_tau, k);
         const unsigned long long tau = s_tau;
         const uint32_t tau_ord = (uint32_t)(tau >> 32);
-        float x[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const long long col = c0 + j * 256 + threadIdx.x;
-            x[j] = col < c_hi ? v[col] : 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < PER; j++) {
             const long long col = c0 + j * 256 + threadIdx.x;
             bool pass = false;
             unsigned long long key = 0;
@@ -1106,6 +1111,8 @@ dense_topk_kernel(const float* __restrict__ values, long long n, long long ld, i
             }
         }
         __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; j++) x[j] = nx[j];
     }
     cta_sort_trim(s_list, &s_cnt, &s_tau, k);
     unsigned long long* out = out_keys + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * k;
