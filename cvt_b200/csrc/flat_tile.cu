@@ -16,6 +16,8 @@
 // filter + the shared sorted lists of topk.cuh), whose keys carry the RANK of the row's label.
 // The lane-per-row kernel this replaces streamed every row with 32 different 512-byte-strided loads per request and
 // measured 0.6 T pair-elements/s.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "dist_tile.cuh"
@@ -235,13 +237,21 @@ int ft_dispatch(Ctx* ctx, int metric, int order, const float* x, long long rows,
     B2_FAIL(-1, "flat search: bad metric/order");
 }
 
-constexpr size_t FT_DMAT_BYTES = 128u << 20;
+// bytes of the [queries][rows] distance chunk between the tile kernel and the selection.  Default: see flat_f32_plan.
+static size_t ft_dmat_bytes() {
+    static const size_t v = []() {
+        const char* e = getenv("B200NN_FLAT_CHUNK_MB");
+        const long long mb = e ? atoll(e) : 128;
+        return (size_t)std::max<long long>(1, std::min<long long>(mb, 1024)) << 20;
+    }();
+    return v;
+}
 
 }  // namespace
 
 // how the rows are cut: row chunks (<= 128 MB of distances each) x column slices of the selection -> lists per query
 void flat_f32_plan(int sm_count, long long nq, long long n, long long* chunk_rows, int* n_chunks, int* slices) {
-    long long cr = (long long)(FT_DMAT_BYTES / sizeof(float)) / std::max<long long>(1, nq) / 128 * 128;
+    long long cr = (long long)(ft_dmat_bytes() / sizeof(float)) / std::max<long long>(1, nq) / 128 * 128;
     cr = std::max<long long>(128, std::min<long long>(cr, (n + 127) / 128 * 128));
     *chunk_rows = cr;
     *n_chunks = (int)std::max<long long>(1, (n + cr - 1) / cr);

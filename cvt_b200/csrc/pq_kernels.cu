@@ -974,7 +974,10 @@ ivf_search_topk_kernel(const float* __restrict__ q_rot, long long nq, int D, con
             const float* lut = s_lut + pp * LUTN;
             const long long lo = list_off[vw], hi = list_off[vw + 1];
             for (long long r0 = lo; r0 < hi; r0 += blockDim.x) {  // CTA-uniform passes of 256 rows
-                if (s_cnt > BUF - (int)blockDim.x) sort_and_trim();  // CTA-uniform: s_cnt only changes between barriers
+                // same decision in every thread: read the counter, barrier, only then may anyone append (see dense_topk_kernel)
+                const int cnt0 = s_cnt;
+                __syncthreads();
+                if (cnt0 > BUF - (int)blockDim.x) sort_and_trim();
                 const unsigned long long tau = s_tau;
                 const long long r = r0 + threadIdx.x;
                 bool pass = false;
@@ -1062,11 +1065,12 @@ __global__ void frame_sum_kernel(const float* scores, int n_frames, long long ng
 __global__ void __launch_bounds__(256)
 dense_topk_kernel(const float* __restrict__ values, long long n, long long ld, int k, const uint32_t* __restrict__ id_map,
                   unsigned long long* __restrict__ out_keys) {
-    // passes of 2048 columns, eight coalesced loads per thread, the NEXT pass's loads already in flight while this one is
-    // filtered (the matrix comes from DRAM: the kernel is bound by bytes in flight); a value meets the threshold's SCORE first
-    // and only a survivor fetches its id; survivors go to the CTA buffer (cta_sort_trim): one sort after the first pass sets
-    // the threshold, after which a pass rarely holds a candidate at all.
-    constexpr int PER = 8, PASS = PER * 256, BUF = 2 * PASS;
+    // passes of 1024 columns, four coalesced loads per thread, the NEXT pass's loads already in flight while this one is
+    // filtered (the matrix comes from DRAM: the kernel is bound by bytes in flight; eight loads per thread with a 32 KB
+    // buffer measured slower); a value meets the threshold's SCORE first and only a survivor fetches its id; survivors go
+    // to the CTA buffer (cta_sort_trim): one sort after the first pass sets the threshold, after which a pass rarely holds
+    // a candidate at all.
+    constexpr int PER = 4, PASS = PER * 256, BUF = 2 * PASS;
     __shared__ __align__(16) unsigned long long s_list[BUF];
     __shared__ unsigned long long s_tau;
     __shared__ int s_cnt;
@@ -1086,9 +1090,15 @@ dense_topk_kernel(const float* __restrict__ values, long long n, long long ld, i
     __syncthreads();
     for (long long c0 = c_lo; c0 < c_hi; c0 += PASS) {
         if (c0 + PASS < c_hi) fetch(nx, c0 + PASS);
-        // CTA-uniform: s_cnt and s_tau only change between barriers
-        if (s_cnt > BUF - PASS || (s_tau == KEY_MAX && s_cnt >= k)) cta_sort_trim(s_list, &s_cnt, &s_tau, k);
-        const unsigned long long tau = s_tau;
+        // The decision to sort must be the same in every thread: all read the counter first, THEN a barrier, and only
+        // then may anyone append (a fast warp's appends of this pass would otherwise be seen by a slow warp's test).
+        const int cnt0 = s_cnt;
+        unsigned long long tau = s_tau;
+        __syncthreads();
+        if (cnt0 > BUF - PASS || (tau == KEY_MAX && cnt0 >= k)) {
+            cta_sort_trim(s_list, &s_cnt, &s_tau, k);
+            tau = s_tau;
+        }
         const uint32_t tau_ord = (uint32_t)(tau >> 32);
 #pragma unroll
         for (int j = 0; j < PER; j++) {

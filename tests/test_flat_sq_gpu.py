@@ -199,6 +199,13 @@ def test_u8_tensor_core_scan_vs_oracle_and_dp4a(ctx, D, n, nq, k, hi):
     finally:
         os.environ.pop("B200NN_NO_TC_U8", None)
     assert np.array_equal(Lt, Ld) and np.array_equal(Dt, Dd)
+    if n >= 262_144:  # the one-pass shared-bound scan (default when k <= 32) == the three passes with running thresholds
+        os.environ["B200NN_U8_NO_SHARED_BOUND"] = "1"
+        try:
+            D3, L3 = idx.search(qu, k)
+        finally:
+            os.environ.pop("B200NN_U8_NO_SHARED_BOUND", None)
+        assert np.array_equal(Lt, L3) and np.array_equal(Dt, D3)
     sel = range(nq) if n <= 5000 else range(0, nq, 9)
     for i in sel:
         od, ol = orc.flat_search(2, 0, xu, labels, qu[i:i + 1], k)

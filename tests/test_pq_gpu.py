@@ -353,3 +353,50 @@ def test_reference_index_shape_K8192_end_to_end(ctx):
         assert np.array_equal(Ig[i].astype(np.int64), oi), i
         assert np.array_equal(_bits(Dg[i]), _bits(os_)), i
     idx.close(); idx2.close()
+
+
+def test_ivf_long_lists_buffer_overflow_path(ctx):
+    """f-1 with LONG lists (K = 4 lists over 20 000 rows, nprobe = 3, no clamp: ~15 000 candidates per query): the CTA-wide
+    candidate buffer of ivf_search_topk_kernel overflows many times and is sorted/trimmed on the way (cta_sort_trim), and the
+    LUTs of the three probes are built in one codebook pass == the oracle's dense restatement, ids and score bits."""
+    from cvt_b200 import capi
+    n, D, M, K, k = 20_000, 64, 8, 4, 100
+    db = synth.sift_like(n, D, seed=31)
+    q = synth.sift_like(24, D, seed=32)
+    perm = synth.random_permutation(D, seed=33)
+    coarse, cb = synth.train_pq_model(db[:, perm], M, 256, K, iters=3, seed=34, train_rows=1500)
+    for clamp in (np.inf, 1.0):
+        idx = capi.PQIndex.create(ctx, coarse, cb, perm=perm, clamp=clamp)
+        idx.add(db)
+        lists, groups, codes = idx.get_rows()
+        assert np.bincount(lists, minlength=K).max() > 2048, "the case must hold lists longer than the candidate buffer"
+        qr = orc.opq_reorder(q, perm)
+        for nprobe in (1, 3):
+            Dg, Ig = idx.search(q, k=k, nprobe=nprobe)
+            dense = orc.opq_query_scores(qr, coarse, cb, nprobe, lists, groups, codes, n, clamp)
+            for i in range(len(q)):
+                os_, oi = orc.topk_pairs(dense[i], k)
+                assert np.array_equal(Ig[i].astype(np.int64), oi), (clamp, nprobe, i)
+                assert np.array_equal(_bits(Dg[i]), _bits(os_)), (clamp, nprobe, i)
+        idx.close()
+
+
+@pytest.mark.parametrize("M,n,nq,k", [(16, 70_001, 300, 100), (32, 40_003, 130, 64), (8, 30_000, 77, 10)])
+def test_scan_kernel_variants_agree(ctx, M, n, nq, k, monkeypatch):
+    """B200NN_SCAN_VAR: round 1's per-block threshold test (0), the two-slot code ring (bit 0, M = 32 only) and the grouped
+    test (bit 1, the default) are the same function of their inputs: ids and score bits identical, and equal to the oracle."""
+    D = 128
+    idx, db, perm, coarse, cb = _random_flat_index(ctx, n, D, M, seed=3000 + M, clamp=1.0)
+    q = synth.sift_like(nq, D, seed=55 + M)
+    res = {}
+    for var in ((0, 1, 2, 3) if M == 32 else (0, 2)):
+        monkeypatch.setenv("B200NN_SCAN_VAR", str(var))
+        res[var] = idx.search(q, k=k, nprobe=1)
+    monkeypatch.delenv("B200NN_SCAN_VAR")
+    res["default"] = idx.search(q, k=k, nprobe=1)
+    _, _, codes = idx.get_rows()
+    od, oi = orc.opq_search_flat(orc.opq_reorder(q[:16], perm), coarse[0], cb, codes, k, clamp=1.0)
+    for var, (Dg, Ig) in res.items():
+        assert np.array_equal(Ig, res[0][1]) and np.array_equal(_bits(Dg), _bits(res[0][0])), var
+        assert np.array_equal(Ig[:16].astype(np.int64), oi) and np.array_equal(_bits(Dg[:16]), _bits(od)), var
+    idx.close()
