@@ -67,3 +67,35 @@ def test_shared_bound_is_valid_and_ties_are_kept():
             assert bound >= true_kth, (trial, L, k, frac)
             # the filter keeps d <= bound: every row of the true top-k (incl. all rows tied at the k-th distance) survives
             assert np.all(d[d <= true_kth] <= bound)
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+@pytest.mark.parametrize("two_slot", [False, True])
+def test_code_ring_schedule_never_overwrites_a_stage_in_use(G, two_slot):
+    """adc_scan_topk_kernel's per-warp code ring (pq_kernels.cu, ScanCfg): lane group h reads block Bg - h while group 0 is at
+    block Bg.  Three-slot ring: stage s+1 is requested at the START of stage s into the slot that held stage s-2.  Two-slot ring
+    (VAR bit 0, M = 32): stage s+1 is requested in the MIDDLE of stage s into the slot that held stage s-1.  At the moment of
+    every request no lane group may still have blocks of the overwritten stage ahead of it, and every block must be read
+    from the slot that holds its stage."""
+    if two_slot and G != 8:
+        pytest.skip("the two-slot ring is only instantiated for G = 8")
+    stage_blocks = 16 if (G <= 4 or two_slot) else 8
+    slots = 2 if two_slot else 3
+    n_st = 9
+    holds = {0: 0}  # slot -> stage (stage 0 is requested before the loop)
+    for st in range(n_st):
+        for bb in range(stage_blocks):
+            Bg = st * stage_blocks + bb
+            request_now = (bb == stage_blocks // 2) if two_slot else (bb == 0)
+            if request_now and st + 1 < n_st:
+                slot = (st + 1) % slots
+                victim = holds.get(slot)
+                if victim is not None:
+                    for h in range(G):  # blocks this group has still to read, from its current one on
+                        cur = Bg - h
+                        assert cur >= (victim + 1) * stage_blocks, (G, two_slot, st, bb, h)
+                holds[slot] = st + 1
+            for h in range(G):
+                b = Bg - h
+                if b >= 0:
+                    assert holds[(b // stage_blocks) % slots] == b // stage_blocks, (G, two_slot, st, bb, h)

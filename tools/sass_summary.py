@@ -16,7 +16,6 @@ print("# UTCIMMA/UTCHMMA = tcgen05.mma kind::i8 / kind::tf32, LDTM = tcgen05.ld,
 print("# SYNCS = mbarrier ops.  No UTMALDG/UTMASTG: every TMA transfer here is a 1-D bulk copy of a contiguous plane/tile (no tensor maps).")
 for obj in sorted(glob.glob(os.path.join(ROOT, "cvt_b200", "lib", "obj", "*.o"))):
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
-    names = subprocess.run(["cuobjdump", "-elf", obj], capture_output=True, text=True).stdout  # unused, kept cheap
     cur, counts = None, collections.OrderedDict()
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)
